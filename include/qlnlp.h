@@ -1,0 +1,141 @@
+/*
+ * qlnlp.h -- C ABI of the B200 batched evaluator for the planar-quadruped landing NLP.
+ *
+ * This is the drop-in boundary: a host program (the reference's Julia `HybridNLP`, a Python
+ * harness, Ipopt's C interface, ...) binds exactly these symbols.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference checkout's src/).
+ * INTEGRATION.md shows the `ccall` methods a maintainer adds next to src/moi.jl.
+ *
+ * Conventions
+ *   - plain C types only; all arrays are fp64 / int64, caller-owned, never retained;
+ *   - every function returns 0 on success, a QLNLP_E* code otherwise, and never throws or exits;
+ *     qlnlp_last_error() returns a message for the calling thread's last failure;
+ *   - indices handed to the caller are 1-BASED (Julia / MOI convention, moi.jl:31-33);
+ *   - one handle may be driven by one host thread at a time (Ipopt calls back from one thread);
+ *     different handles are independent;
+ *   - there is NO CPU fallback: evaluation entry points fail with QLNLP_ENODEVICE when no
+ *     sm_100 device / driver is present.  Structure, dimension and bound queries are pure host
+ *     integer logic and work anywhere.
+ *
+ * Layouts
+ *   Z     n_nlp = 20N-5        knot k (1-based): x_k at 20(k-1)+1..+15, u_k at 20(k-1)+16..+20   nlp.jl:38-39
+ *   g     m_nlp = 18N-k_trans+16   blocks init|term|dyn|contact-first|contact-other|final-ctrl|body-pos   nlp.jl:48-63
+ *   grad  n_nlp
+ *   jac   QLNLP_JAC_SPARSE_BLOCK: nnz = 529N-k_trans-87 values = the entries constraints.jl:212-291
+ *         assigns, in the reference's column-major order (row fastest);
+ *         QLNLP_JAC_DENSE: the full m_nlp x n_nlp column-major grid the reference reports
+ *         (moi.jl:31-33), unassigned entries written as 0 -- single evaluations only.
+ */
+#ifndef QLNLP_H
+#define QLNLP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QLNLP_VERSION 1
+
+enum {
+    QLNLP_OK = 0,
+    QLNLP_EINVAL = 1,     /* bad argument (NULL, out-of-range N/k_trans/init_mode, misaligned ld) */
+    QLNLP_ENODEVICE = 2,  /* no usable CUDA device / driver: the product has no CPU path */
+    QLNLP_ECUDA = 3,      /* a CUDA runtime call failed; see qlnlp_last_error() */
+    QLNLP_ENOMEM = 4
+};
+
+enum {
+    QLNLP_JAC_SPARSE_BLOCK = 0,
+    QLNLP_JAC_DENSE = 1
+};
+
+/* planar_quadruped.jl:11-20 */
+typedef struct {
+    double g, mb, mf, lb, l1, l2;
+} qlnlp_model;
+
+/* The fields of HybridNLP (nlp.jl:13-33) the evaluators read, plus the per-knot QuadraticCost
+ * tables (quadratic_cost.jl:16-22; Q and R as diagonals), knot-major, N rows each; row N-1 is the
+ * terminal cost (costs.jl:15,33). */
+typedef struct {
+    int64_t N;          /* knot points                                  nlp.jl:16 */
+    int64_t k_trans;    /* first knot of mode 3, 1 <= k_trans <= N      nlp.jl:19 */
+    int64_t init_mode;  /* 1 or 2                                       nlp.jl:18 */
+    qlnlp_model model;
+    double x0[15];      /* nlp.jl:20 */
+    double xf[15];      /* nlp.jl:21 */
+    const double* Q;    /* [N][15] */
+    const double* R;    /* [N][5]  */
+    const double* q;    /* [N][15] */
+    const double* r;    /* [N][5]  */
+    const double* c;    /* [N]     */
+} qlnlp_problem_desc;
+
+typedef struct qlnlp_handle_s* qlnlp_handle;
+
+/* HybridNLP(model, obj, init_mode, k_trans, N, x0, xf)            nlp.jl:33-83
+ * `device` is the CUDA ordinal used by every later call on the handle (bound lazily, at the first
+ * evaluation).  `jac_mode` selects what qlnlp_eval_constraint_jacobian / jacobian_structure report. */
+int qlnlp_create(const qlnlp_problem_desc* desc, int device, int jac_mode, qlnlp_handle* out);
+int qlnlp_destroy(qlnlp_handle h);
+
+/* num_primals / num_duals                                          nlp.jl:86-87
+ * nnz = length of the structure for the handle's jac_mode; nnz_block = SPARSE_BLOCK count. */
+int qlnlp_dims(qlnlp_handle h, int64_t* n_nlp, int64_t* m_nlp, int64_t* nnz, int64_t* nnz_block);
+
+/* MOI.jacobian_structure(nlp)                                      moi.jl:31-33
+ * Fills rows[nnz], cols[nnz], 1-based, in value order.  Host-only integer logic. */
+int qlnlp_jacobian_structure(qlnlp_handle h, int64_t* rows, int64_t* cols);
+
+/* constraint bounds nlp.lb / nlp.ub                                nlp.jl:66-69 */
+int qlnlp_constraint_bounds(qlnlp_handle h, double* lb, double* ub);
+/* the variable bounds solve() installs                             moi.jl:51-67 */
+int qlnlp_variable_bounds(qlnlp_handle h, double* xl, double* xu);
+
+/* ---- single evaluations on HOST pointers: the four MOI callbacks ------------------------- */
+/* MOI.eval_objective(prob, x)               -> eval_f              moi.jl:1-3   costs.jl:6-16 */
+int qlnlp_eval_objective(qlnlp_handle h, const double* x, double* f);
+/* MOI.eval_objective_gradient(prob, grad, x) -> grad_f!            moi.jl:5-8   costs.jl:23-34 */
+int qlnlp_eval_objective_gradient(qlnlp_handle h, const double* x, double* grad);
+/* MOI.eval_constraint(prob, g, x)           -> eval_c!             moi.jl:10-13 constraints.jl:145-158 */
+int qlnlp_eval_constraint(qlnlp_handle h, const double* x, double* g);
+/* MOI.eval_constraint_jacobian(prob, vals, x) -> jac_c!            moi.jl:15-24 constraints.jl:212-291
+ * vals has qlnlp_dims().nnz entries in jacobian_structure order. */
+int qlnlp_eval_constraint_jacobian(qlnlp_handle h, const double* x, double* vals);
+
+/* ---- batched evaluation (B independent decision vectors; no reference equivalent) -------- */
+typedef struct {
+    const double* Z;   int64_t ldz;     /* [B][ldz],    ldz    >= n_nlp          (required) */
+    const double* x0;                   /* [B][15] per-evaluation initial state, or NULL -> desc.x0 */
+    const double* xf;                   /* [B][15] per-evaluation final state,   or NULL -> desc.xf */
+    double* f;                          /* [B]                                    or NULL: skip */
+    double* grad;      int64_t ldgrad;  /* [B][ldgrad], ldgrad >= n_nlp           or NULL: skip */
+    double* g;         int64_t ldg;     /* [B][ldg],    ldg    >= m_nlp           or NULL: skip */
+    double* jac;       int64_t ldjac;   /* [B][ldjac],  ldjac  >= nnz_block       or NULL: skip
+                                           SPARSE_BLOCK values.  The TMA bulk-store path needs jac
+                                           16-byte aligned and ldjac even; otherwise a slower
+                                           plain-store path is used. */
+} qlnlp_batch_io;
+
+/* All pointers are DEVICE pointers on the handle's device; the launch is enqueued on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream) and the call returns without
+ * synchronising.  One fused kernel evaluates everything requested. */
+int qlnlp_eval_batch_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, void* stream);
+
+/* All pointers are HOST pointers.  Copies Z (and x0/xf) to the device, evaluates, copies the
+ * requested outputs back, and returns when they are in place.  Work is pipelined in chunks over
+ * two streams so copies overlap the kernel. */
+int qlnlp_eval_batch_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io);
+
+/* Launch geometry of the last batched launch (for benchmarks / profiles): blocks, threads per
+ * block, dynamic shared memory per block, resident blocks per SM, SM count. */
+int qlnlp_launch_info(qlnlp_handle h, int64_t info[5]);
+
+const char* qlnlp_last_error(void);
+int qlnlp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,15 @@
+"""B200-native batched evaluator for the planar-quadruped landing NLP.
+
+The package holds only what the hot path needs: the CUDA kernels + C ABI (``csrc/``,
+``include/qlnlp.h``), the in-tree build, the host-side problem tables, and ``HybridNLP``, the
+host-side mirror of the reference's ``MOI.AbstractNLPEvaluator`` surface (src/nlp.jl, src/moi.jl).
+"""
+from .problem import (NX, NU, PlanarQuadruped, QuadraticCost, LQRCost, ProblemData, reference_trajectory,
+                      packZ, unpackZ, default_states, build_problem, default_problem, initial_guess)
+from .evaluator import HybridNLP, QlnlpError, load_library, even_ld, EXPORTED_SYMBOLS
+
+__all__ = [
+    "NX", "NU", "PlanarQuadruped", "QuadraticCost", "LQRCost", "ProblemData", "reference_trajectory",
+    "packZ", "unpackZ", "default_states", "build_problem", "default_problem", "initial_guess",
+    "HybridNLP", "QlnlpError", "load_library", "even_ld", "EXPORTED_SYMBOLS",
+]

@@ -1,0 +1,347 @@
+// qlnlp_kernels.cuh -- fused batched evaluator kernel for sm_100a (B200).
+//
+// One warp per trajectory (decision vector), one lane per knot, ceil(N/32) passes; one warp per
+// CTA so warps never synchronise with each other.  Per evaluation the warp
+//   1. stages Z through shared memory (cp.async, coalesced 8-byte elements, knot stride padded
+//      to 21 doubles so the lane-per-knot reads are bank-conflict free),
+//   2. evaluates, per lane, the quadratic stage cost + gradient (costs.jl:6-34), one RK4 step of
+//      the hybrid dynamics and its defect (constraints.jl:6-41), the contact / final-force /
+//      body-clearance rows (constraints.jl:48-113,154) and the structurally non-zero entries of
+//      the 15x20 RK4 Jacobian by forward-mode duals held in registers (rk4_dual_gen.h),
+//   3. writes g/grad through small shared staging tiles with coalesced stores, reduces the cost
+//      over the warp with shuffles,
+//   4. streams the SPARSE_BLOCK Jacobian values: the value stream is a concatenation of per-knot
+//      runs (layout.h) that are >85 % structural constants, so each 1-2-knot segment lives in a
+//      shared-memory image whose constants persist from one evaluation to the next; the owner
+//      lanes patch only the value-dependent entries and one lane fires a TMA bulk store
+//      (cp.async.bulk.global.shared::cta, SASS UBLKCP) of the whole 4-8 KB segment.
+// All arithmetic is fp64 with explicit round-to-nearest add/mul/div (no FMA contraction) in the
+// reference's operation order, so g, grad and the Jacobian values are bit-identical to the CPU
+// oracle; only the cost reduction order (warp tree vs. sequential) differs.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+
+namespace ql {
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ unsigned smem_addr(const void* p)
+{
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void st_shared_f64(unsigned addr, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_zero16(unsigned addr)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(addr), "d"(0.0) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(unsigned dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// TMA bulk copy shared::cta -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void* gdst, unsigned ssrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace ql
+
+// generated RK4 + Jacobian code: explicit rounding, shared-memory patch stores
+#define QL_ADD(a, b) __dadd_rn((a), (b))
+#define QL_SUB(a, b) __dsub_rn((a), (b))
+#define QL_MUL(a, b) __dmul_rn((a), (b))
+#define QL_DIV(a, b) __ddiv_rn((a), (b))
+#define QL_FN __device__ __forceinline__
+#define QL_ST(ptr, off, val) ql::st_shared_f64((ptr) + 8u * (off), (val))
+#include "rk4_dual_gen.h"
+
+namespace ql {
+
+#define QL_NJ_MAX (QL_NJ_MODE1 > QL_NJ_MODE3 ? QL_NJ_MODE1 : QL_NJ_MODE3)
+
+struct Launch {
+    QlClass c;
+    const double* cost;        // [QL_NCOST][npad] field-major: Q 0-14, q 15-29, R 30-34, r 35-39, c 40
+    int npad;
+    const double* x0_def;      // [15]  desc.x0
+    const double* xf_def;      // [15]  desc.xf
+    const QlSeg* segs;         // segment plan, all passes
+    const int* seg_begin;      // [npass + 1]
+    const double* Z; long long ldz;
+    const double* x0;          // [B][15] or nullptr
+    const double* xf;          // [B][15] or nullptr
+    double* f;
+    double* grad; long long ldgrad;
+    double* g; long long ldg;
+    double* jac; long long ldjac;
+    long long B;
+    int bulk;                  // 1: jac rows are 16 B aligned -> TMA bulk stores
+};
+
+// shared memory carve-up (doubles)
+__host__ __device__ inline int zbuf_len(int N) { return (QL_ZSTRIDE * N + 1) & ~1; }
+constexpr int GD_LEN = QL_LANES * QL_NX;        // dynamics defects of one pass
+constexpr int GR_LEN = QL_LANES * QL_ZSTRIDE;   // gradient of one pass (knot stride padded to 21)
+__host__ __device__ inline size_t smem_bytes(int N, bool with_jac)
+{
+    return sizeof(double) * (size_t)(zbuf_len(N) + GD_LEN + GR_LEN + (with_jac ? 2 * QL_JBUF : 0));
+}
+
+// cp.async the decision vector into the padded shared layout (element e -> e + e/20)
+__device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigned zaddr, int n, int lane)
+{
+    for (int e = lane; e < n; e += QL_LANES) cp_async_8(zaddr + 8u * (unsigned)(e + e / QL_NZK), Zrow + e);
+    cp_async_commit();
+}
+
+template <bool WITH_JAC>
+__global__ void __launch_bounds__(QL_LANES) eval_kernel(const __grid_constant__ Launch P)
+{
+    extern __shared__ __align__(16) double smem[];
+    const QlClass& c = P.c;
+    const int lane = threadIdx.x;
+
+    double* const zbuf = smem;
+    double* const gd = zbuf + zbuf_len(c.N);
+    double* const gr = gd + GD_LEN;
+    double* const jb = gr + GR_LEN;
+    const unsigned zaddr = smem_addr(zbuf);
+    const unsigned jaddr = smem_addr(jb);
+    int tmpl0 = -1, tmpl1 = -1;        // template currently held by staging buffer 0 / 1
+
+    const double mg = c.g, mb = c.mb, mf = c.mf, Ib = c.Ib;
+    const bool first_is_y1 = (c.init_mode == 1);    // contact-first reads y1 (mode 1) or y2 (mode 2)
+
+    long long b = blockIdx.x;
+    if (b < P.B) stage_z(P.Z + b * P.ldz, zaddr, c.n_nlp, lane);
+
+    for (; b < P.B; b += gridDim.x) {
+        cp_async_wait_all();
+        __syncwarp();
+        double fsum = 0.0;
+        double* const grow = P.g ? P.g + b * P.ldg : nullptr;
+        double* const gradrow = P.grad ? P.grad + b * P.ldgrad : nullptr;
+        double* const jrow = WITH_JAC ? P.jac + b * P.ldjac : nullptr;
+
+        for (int p = 0; p < c.npass; ++p) {
+            const int k = p * QL_LANES + lane + 1;          // 1-based knot of this lane
+            const bool act = k <= c.N;
+            const bool has_u = k < c.N;
+            const bool jump = has_u && (k == c.k_trans - 1);   // constraints.jl:29 / :190
+
+            // ---- 1. my knot's slice of Z: x_k, u_k, x_{k+1}
+            double xk[QL_NX], uk[QL_NU], xnx[QL_NX];
+            {
+                const double* zk = zbuf + (k - 1) * QL_ZSTRIDE;
+#pragma unroll
+                for (int i = 0; i < QL_NX; ++i) xk[i] = act ? zk[i] : 0.0;
+#pragma unroll
+                for (int i = 0; i < QL_NU; ++i) uk[i] = has_u ? zk[QL_NX + i] : 0.0;
+#pragma unroll
+                for (int i = 0; i < QL_NX; ++i) xnx[i] = has_u ? zk[QL_ZSTRIDE + i] : 0.0;
+            }
+            if (p == c.npass - 1) {
+                // every lane holds its inputs: prefetch the next decision vector over this one
+                __syncwarp();
+                const long long nb = b + gridDim.x;
+                if (nb < P.B) stage_z(P.Z + nb * P.ldz, zaddr, c.n_nlp, lane);
+            }
+
+            // ---- 2. cost and gradient (costs.jl:6-34, quadratic_cost.jl:44-52)
+            if (act && (P.f || gradrow)) {
+                const double* ct = P.cost + (k - 1);
+                const int np = P.npad;
+                double hq, dq;
+                {
+                    const double Q0 = __ldg(ct), q0 = __ldg(ct + 15 * np);
+                    hq = __dmul_rn(__dmul_rn(0.5, __dmul_rn(xk[0], Q0)), xk[0]);     // 0.5*x'Q*x, folded left
+                    dq = __dmul_rn(q0, xk[0]);                                        // q'x
+                    const double gq = __dadd_rn(__dmul_rn(Q0, xk[0]), q0);            // Q*x + q
+                    gr[lane * QL_ZSTRIDE] = has_u ? __dmul_rn(uk[4], gq) : gq;
+                }
+#pragma unroll
+                for (int i = 1; i < QL_NX; ++i) {
+                    const double Qi = __ldg(ct + i * np), qi = __ldg(ct + (15 + i) * np);
+                    hq = __dadd_rn(hq, __dmul_rn(__dmul_rn(0.5, __dmul_rn(xk[i], Qi)), xk[i]));
+                    dq = __dadd_rn(dq, __dmul_rn(qi, xk[i]));
+                    const double gq = __dadd_rn(__dmul_rn(Qi, xk[i]), qi);
+                    gr[lane * QL_ZSTRIDE + i] = has_u ? __dmul_rn(uk[4], gq) : gq;
+                }
+                const double cc = __ldg(ct + 40 * np);
+                double term;
+                if (has_u) {
+                    const double R0 = __ldg(ct + 30 * np), r0 = __ldg(ct + 35 * np);
+                    double hr = __dmul_rn(__dmul_rn(0.5, __dmul_rn(uk[0], R0)), uk[0]);
+                    double dr = __dmul_rn(r0, uk[0]);
+                    gr[lane * QL_ZSTRIDE + QL_NX] = __dmul_rn(uk[4], __dadd_rn(__dmul_rn(R0, uk[0]), r0));
+#pragma unroll
+                    for (int i = 1; i < QL_NU; ++i) {
+                        const double Ri = __ldg(ct + (30 + i) * np), ri = __ldg(ct + (35 + i) * np);
+                        hr = __dadd_rn(hr, __dmul_rn(__dmul_rn(0.5, __dmul_rn(uk[i], Ri)), uk[i]));
+                        dr = __dadd_rn(dr, __dmul_rn(ri, uk[i]));
+                        // quirk Q1 (costs.jl:30): the h entry gets h*(R55*h + r5), not d(h*stagecost)/dh
+                        gr[lane * QL_ZSTRIDE + QL_NX + i] = __dmul_rn(uk[4], __dadd_rn(__dmul_rn(Ri, uk[i]), ri));
+                    }
+                    // ((((0.5x'Qx + q'x) + 0.5u'Ru) + r'u) + c) * h
+                    const double sc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(hq, dq), hr), dr), cc);
+                    term = __dmul_rn(uk[4], sc);
+                } else {
+                    term = __dadd_rn(__dadd_rn(hq, dq), cc);       // termcost
+                }
+                fsum += term;
+            }
+
+            // ---- 3. constraints (constraints.jl:145-158) and the RK4 Jacobian values
+            double jv[WITH_JAC ? QL_NJ_MAX : 1];
+            double jtheta = 0.0;
+            if (has_u && (WITH_JAC || grow)) {
+                double xn[QL_NX];
+                if (WITH_JAC) {
+                    if (k >= c.k_trans) ql_rk4_jac_mode3(xk, uk, mg, mb, mf, Ib, xn, jv);
+                    else if (c.init_mode == 1) ql_rk4_jac_mode1(xk, uk, mg, mb, mf, Ib, xn, jv);
+                    else ql_rk4_jac_mode2(xk, uk, mg, mb, mf, Ib, xn, jv);
+                } else {
+                    if (k >= c.k_trans) ql_rk4_mode3(xk, uk, mg, mb, mf, Ib, xn);
+                    else if (c.init_mode == 1) ql_rk4_mode1(xk, uk, mg, mb, mf, Ib, xn);
+                    else ql_rk4_mode2(xk, uk, mg, mb, mf, Ib, xn);
+                }
+                if (jump) {   // jump1_map / jump2_map, planar_quadruped.jl:250-260
+                    xn[4] = 0.0; xn[6] = 0.0; xn[10] = 0.0; xn[11] = 0.0; xn[12] = 0.0; xn[13] = 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < QL_NX; ++i) gd[lane * QL_NX + i] = __dsub_rn(xn[i], xnx[i]);
+            }
+            if (act && (WITH_JAC || grow)) {
+                double s, co;
+                sincos(xk[2], &s, &co);
+                // quirk Q4 (constraints.jl:269-273): branch on theta > 0
+                jtheta = (xk[2] > 0) ? __dmul_rn(-c.half_lb, co) : __dmul_rn(c.half_lb, co);
+                if (grow) {
+                    grow[c.c_cfirst + (k - 1)] = first_is_y1 ? xk[4] : xk[6];                                   // :58/:60
+                    if (k >= c.k_trans) grow[c.c_cother + (k - c.k_trans)] = first_is_y1 ? xk[6] : xk[4];      // :84/:86
+                    grow[c.c_body + (k - 1)] = __dsub_rn(xk[1], __dmul_rn(c.half_lb, fabs(s)));   // :109
+                    if (k == 1) {
+                        const double* x0 = P.x0 ? P.x0 + b * QL_NX : P.x0_def;
+#pragma unroll
+                        for (int i = 0; i < QL_NX; ++i) grow[i] = __dsub_rn(xk[i], __ldg(x0 + i));        // :149
+                    }
+                    if (k == c.N) {
+                        const double* xf = P.xf ? P.xf + b * QL_NX : P.xf_def;
+#pragma unroll
+                        for (int i = 0; i < QL_NX - 1; ++i) grow[c.c_term + i] = __dsub_rn(xk[i], __ldg(xf + i));   // :150
+                    }
+                    if (k == c.N - 1) grow[c.c_fctrl] = __dadd_rn(__dadd_rn(uk[1], uk[3]), c.mbg);       // :154
+                }
+            }
+
+            // ---- 4. flush the pass tiles with coalesced stores
+            __syncwarp();
+            if (grow) {
+                const int k_first = p * QL_LANES + 1;
+                const int ndyn = min(QL_LANES, c.N - k_first) * QL_NX;      // knots k_first.. with k < N
+                double* dst = grow + c.c_dyn + (k_first - 1) * QL_NX;
+                for (int i = lane; i < ndyn; i += QL_LANES) dst[i] = gd[i];
+            }
+            if (gradrow) {
+                const int e0 = p * QL_LANES * QL_NZK;
+                const int cnt = min(QL_LANES * QL_NZK, c.n_nlp - e0);
+                for (int i = lane; i < cnt; i += QL_LANES) gradrow[e0 + i] = gr[i + i / QL_NZK];
+            }
+            __syncwarp();
+
+            // ---- 5. stream this pass's share of the Jacobian values
+            if (WITH_JAC) {
+                const int roff = act ? ql_run_off(c, k) : 0;
+                const int sb = __ldg(P.seg_begin + p), se = __ldg(P.seg_begin + p + 1);
+                for (int s = sb; s < se; ++s) {
+                    const int4 s0 = __ldg(reinterpret_cast<const int4*>(P.segs + s));          // k0 nk start end
+                    const int4 s1 = __ldg(reinterpret_cast<const int4*>(P.segs + s) + 1);      // tmpl buf - -
+                    const int k0 = s0.x, nk = s0.y, start = s0.z, end = s0.w, tm = s1.x, bi = s1.y;
+                    double* const buf = jb + bi * QL_JBUF;
+                    const unsigned baddr = jaddr + (unsigned)bi * (QL_JBUF * 8u);
+                    const int base = start & ~1;                 // image[0] <-> stream offset `base`
+                    const bool mine = act && k >= k0 && k < k0 + nk;
+
+                    // the bulk store issued two segments ago read this buffer: wait until it is done
+                    if (P.bulk && lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+
+                    if ((bi ? tmpl1 : tmpl0) != tm) {            // different constant image: rebuild
+                        for (int i = lane; i < QL_JBUF / 2; i += QL_LANES) st_shared_zero16(baddr + 16u * i);
+                        __syncwarp();
+                        if (mine) ql_write_run_constants(c, k, buf + (roff - base));
+                        if (bi) tmpl1 = tm; else tmpl0 = tm;
+                    }
+                    if (mine) {
+                        const unsigned raddr = baddr + 8u * (unsigned)(roff - base);
+                        if (has_u) {
+                            const int e4 = ql_e4(c, k), e6 = ql_e6(c, k), fc = ql_fc(c, k);
+                            unsigned pg[7];
+                            pg[0] = raddr;
+                            pg[1] = raddr + 8u;
+                            pg[2] = raddr + 16u;
+                            pg[3] = raddr + 8u * (2 + e4);
+                            pg[4] = raddr + 8u * (2 + e4 + e6);
+                            pg[5] = raddr + 8u * (2 + e4 + e6 + fc);
+                            pg[6] = raddr + 8u * (2 + e4 + e6 + 2 * fc);
+                            if (k >= c.k_trans) ql_patch_mode3(jv, pg, jump);
+                            else if (c.init_mode == 1) ql_patch_mode1(jv, pg, jump);
+                            else ql_patch_mode2(jv, pg, jump);
+                        }
+                        st_shared_f64(raddr + 8u * (unsigned)ql_theta_pos(c, k), jtheta);   // constraints.jl:269-273
+                    }
+                    if (P.bulk) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        const int a = (start + 1) & ~1, e = end & ~1;      // 16 B aligned interior
+                        if (lane == 0) {
+                            if (e > a) bulk_store(jrow + a, baddr + 8u * (unsigned)(a - base), 8u * (unsigned)(e - a));
+                            bulk_commit();
+                        }
+                        if (lane == 1 && (start & 1)) jrow[start] = buf[start - base];
+                        if (lane == 2 && (end & 1)) jrow[end - 1] = buf[end - 1 - base];
+                    } else {
+                        __syncwarp();
+                        for (int i = lane; i < end - start; i += QL_LANES) jrow[start + i] = buf[start - base + i];
+                    }
+                }
+            }
+        }
+
+        // ---- 6. cost: warp-shuffle tree over the per-lane terms (costs.jl:9-15 sums sequentially)
+        if (P.f) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, off);
+            if (lane == 0) P.f[b] = fsum;
+        }
+    }
+    if (WITH_JAC && P.bulk && lane == 0) bulk_wait_all();
+}
+
+// DENSE mode (single evaluations): scatter SPARSE_BLOCK values into the zeroed m x n grid
+__global__ void scatter_dense_kernel(const double* __restrict__ vals, const long long* __restrict__ lin,
+                                     double* __restrict__ dense, int nnz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) dense[lin[i]] = vals[i];
+}
+
+}  // namespace ql

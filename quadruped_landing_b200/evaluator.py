@@ -1,0 +1,353 @@
+"""Host-side mirror of the reference's evaluator interface over the C-ABI CUDA library.
+
+``HybridNLP`` keeps the reference's names and argument meaning (src/nlp.jl:13-114 and the
+``MOI.*`` methods of src/moi.jl:1-33): ``eval_objective``, ``eval_objective_gradient``,
+``eval_constraint``, ``eval_constraint_jacobian``, ``jacobian_structure``,
+``features_available``, ``initialize``, ``num_primals``, ``num_duals``, ``packZ``/``unpackZ``.
+Every numeric call goes through ``libqlnlp.so`` (include/qlnlp.h) and runs on the GPU; there is
+no CPU implementation in this package -- if the library or a B200 is missing the call raises.
+
+Batched evaluation (many decision vectors per launch) has no counterpart in the reference; it
+is exposed as ``eval_batch`` (device tensors, the timed path) and ``eval_batch_host``
+(numpy / pinned host buffers, copies included).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import build as _build
+from .problem import NX, NU, PlanarQuadruped, ProblemData, QuadraticCost, packZ as _packZ, unpackZ as _unpackZ
+
+QLNLP_OK, QLNLP_EINVAL, QLNLP_ENODEVICE, QLNLP_ECUDA, QLNLP_ENOMEM = range(5)
+JAC_SPARSE_BLOCK, JAC_DENSE = 0, 1
+
+# every symbol include/qlnlp.h declares
+EXPORTED_SYMBOLS = (
+    "qlnlp_version", "qlnlp_last_error", "qlnlp_create", "qlnlp_destroy", "qlnlp_dims",
+    "qlnlp_jacobian_structure", "qlnlp_constraint_bounds", "qlnlp_variable_bounds",
+    "qlnlp_eval_objective", "qlnlp_eval_objective_gradient", "qlnlp_eval_constraint",
+    "qlnlp_eval_constraint_jacobian", "qlnlp_eval_batch_device", "qlnlp_eval_batch_host",
+    "qlnlp_launch_info",
+)
+
+
+class QlnlpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"qlnlp error {code}: {msg}")
+        self.code = code
+
+
+class _Model(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("g", "mb", "mf", "lb", "l1", "l2")]
+
+
+class _Desc(C.Structure):
+    _fields_ = [("N", C.c_int64), ("k_trans", C.c_int64), ("init_mode", C.c_int64),
+                ("model", _Model), ("x0", C.c_double * 15), ("xf", C.c_double * 15),
+                ("Q", C.c_void_p), ("R", C.c_void_p), ("q", C.c_void_p), ("r", C.c_void_p), ("c", C.c_void_p)]
+
+
+class _BatchIO(C.Structure):
+    _fields_ = [("Z", C.c_void_p), ("ldz", C.c_int64),
+                ("x0", C.c_void_p), ("xf", C.c_void_p),
+                ("f", C.c_void_p),
+                ("grad", C.c_void_p), ("ldgrad", C.c_int64),
+                ("g", C.c_void_p), ("ldg", C.c_int64),
+                ("jac", C.c_void_p), ("ldjac", C.c_int64)]
+
+
+_lib = None
+
+
+def load_library(rebuild_if_stale: bool = True):
+    """dlopen libqlnlp.so (building it first if the sources are newer).  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if rebuild_if_stale and _build.is_stale():
+        path = _build.build()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m quadruped_landing_b200.build` "
+                           "(the evaluator has no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
+    L.qlnlp_version.restype = C.c_int
+    L.qlnlp_last_error.restype = C.c_char_p
+    L.qlnlp_create.argtypes = [C.POINTER(_Desc), C.c_int, C.c_int, C.POINTER(vp)]
+    L.qlnlp_destroy.argtypes = [vp]
+    L.qlnlp_dims.argtypes = [vp, i64p, i64p, i64p, i64p]
+    L.qlnlp_jacobian_structure.argtypes = [vp, vp, vp]
+    L.qlnlp_constraint_bounds.argtypes = [vp, vp, vp]
+    L.qlnlp_variable_bounds.argtypes = [vp, vp, vp]
+    for name in ("qlnlp_eval_objective", "qlnlp_eval_objective_gradient", "qlnlp_eval_constraint",
+                 "qlnlp_eval_constraint_jacobian"):
+        getattr(L, name).argtypes = [vp, vp, vp]
+    L.qlnlp_eval_batch_device.argtypes = [vp, C.c_int64, C.POINTER(_BatchIO), vp]
+    L.qlnlp_eval_batch_host.argtypes = [vp, C.c_int64, C.POINTER(_BatchIO)]
+    L.qlnlp_launch_info.argtypes = [vp, i64p]
+    L.qlnlp_debug_segments.argtypes = [vp, vp, C.c_int64, i64p]
+    for name in EXPORTED_SYMBOLS[2:] + ("qlnlp_debug_segments",):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != QLNLP_OK:
+        raise QlnlpError(rc, load_library().qlnlp_last_error().decode())
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def even_ld(n: int) -> int:
+    """Leading dimension that keeps every row 16-byte aligned (what the TMA store path needs)."""
+    return (n + 1) & ~1
+
+
+class HybridNLP:
+    """GPU-backed stand-in for the reference's ``HybridNLP`` (src/nlp.jl:13-84).
+
+    ``HybridNLP(model, obj, init_mode, k_trans, N, x0, xf; use_sparse_jacobian)`` -- same argument
+    order as nlp.jl:33-36.  ``use_sparse_jacobian=False`` (the reference's default) reports the
+    dense ``m_nlp x n_nlp`` column-major structure of moi.jl:31-33; ``True`` reports SPARSE_BLOCK,
+    the column-major filter of the entries ``jac_c!`` assigns (the reference's own sparse branch,
+    moi.jl:17-18, is not functional).
+    """
+
+    def __init__(self, model: PlanarQuadruped, obj: Sequence[QuadraticCost], init_mode: int, k_trans: int,
+                 N: int, x0, xf, integration: str = "RK4", *, use_sparse_jacobian: bool = False, device: int = 0):
+        if integration != "RK4":
+            raise ValueError("only RK4 is implemented (as in the reference)")
+        self._init(ProblemData.from_costs(model, obj, init_mode, k_trans, N, x0, xf), use_sparse_jacobian, device)
+
+    @classmethod
+    def from_problem(cls, prob: ProblemData, *, use_sparse_jacobian: bool = True, device: int = 0) -> "HybridNLP":
+        self = cls.__new__(cls)
+        self._init(prob, use_sparse_jacobian, device)
+        return self
+
+    def _init(self, prob: ProblemData, use_sparse_jacobian: bool, device: int):
+        L = load_library()
+        self.prob = prob
+        self.model = prob.model
+        self.N, self.k_trans, self.init_mode = prob.N, prob.k_trans, prob.init_mode
+        self.Nmodes = 2                                   # nlp.jl:45
+        self.x0, self.xf = prob.x0, prob.xf
+        self.modes = [prob.init_mode if k < prob.k_trans else 3 for k in range(1, prob.N + 1)]   # nlp.jl:42-44
+        self.use_sparse_jacobian = bool(use_sparse_jacobian)
+        self.device = int(device)
+        d = _Desc()
+        d.N, d.k_trans, d.init_mode = prob.N, prob.k_trans, prob.init_mode
+        m = prob.model
+        d.model = _Model(m.g, m.mb, m.mf, m.lb, m.l1, m.l2)
+        for i in range(NX):
+            d.x0[i] = float(prob.x0[i])
+            d.xf[i] = float(prob.xf[i])
+        d.Q, d.R, d.q, d.r, d.c = (a.ctypes.data for a in (prob.Q, prob.R, prob.q, prob.r, prob.c))
+        self._h = C.c_void_p()
+        _check(L.qlnlp_create(C.byref(d), self.device, JAC_SPARSE_BLOCK if use_sparse_jacobian else JAC_DENSE,
+                              C.byref(self._h)))
+        n, mm, nnz, nnzb = (C.c_int64() for _ in range(4))
+        _check(L.qlnlp_dims(self._h, C.byref(n), C.byref(mm), C.byref(nnz), C.byref(nnzb)))
+        self.n_nlp, self.m_nlp, self.nnz, self.nnz_block = n.value, mm.value, nnz.value, nnzb.value
+        # index maps, 1-based like nlp.jl:38-39,48-63
+        self.xinds = [np.arange(1, NX + 1) + (k - 1) * (NX + NU) for k in range(1, self.N + 1)]
+        self.uinds = [np.arange(NX + 1, NX + NU + 1) + (k - 1) * (NX + NU) for k in range(1, self.N)]
+        N, kt = self.N, self.k_trans
+        ends = np.cumsum([NX, NX - 1, (N - 1) * NX, N, N - kt + 1, 1, N])
+        self.cinds = [range(int(e - w) + 1, int(e) + 1) for e, w in zip(ends, [NX, NX - 1, (N - 1) * NX, N, N - kt + 1, 1, N])]
+        self.lb, self.ub = self.constraint_bounds()
+        self.zL = np.full(self.n_nlp, -np.inf)           # nlp.jl:73-74
+        self.zU = np.full(self.n_nlp, np.inf)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _lib is not None:
+            _lib.qlnlp_destroy(h)
+            self._h = C.c_void_p()
+
+    # ---- nlp.jl:85-114
+    def size(self) -> Tuple[int, int, int]:
+        return NX, NU, self.N
+
+    def num_primals(self) -> int:
+        return self.n_nlp
+
+    def num_duals(self) -> int:
+        return self.m_nlp
+
+    def packZ(self, X, U) -> np.ndarray:
+        return _packZ(self.N, X, U)
+
+    def unpackZ(self, Z):
+        return _unpackZ(self.N, Z)
+
+    # ---- MOI surface, moi.jl:1-33
+    def features_available(self) -> List[str]:
+        return ["Grad", "Jac"]                            # moi.jl:26-28
+
+    def initialize(self, features: Iterable[str] = ()) -> None:
+        return None                                       # moi.jl:30
+
+    def jacobian_structure(self) -> List[Tuple[int, int]]:
+        rows, cols = self.jacobian_structure_arrays()
+        return list(zip(rows.tolist(), cols.tolist()))
+
+    def jacobian_structure_arrays(self) -> Tuple[np.ndarray, np.ndarray]:
+        rows = np.empty(self.nnz, dtype=np.int64)
+        cols = np.empty(self.nnz, dtype=np.int64)
+        _check(load_library().qlnlp_jacobian_structure(self._h, _np_ptr(rows), _np_ptr(cols)))
+        return rows, cols
+
+    def constraint_bounds(self) -> Tuple[np.ndarray, np.ndarray]:
+        lb, ub = np.empty(self.m_nlp), np.empty(self.m_nlp)
+        _check(load_library().qlnlp_constraint_bounds(self._h, _np_ptr(lb), _np_ptr(ub)))
+        return lb, ub
+
+    def variable_bounds(self) -> Tuple[np.ndarray, np.ndarray]:
+        xl, xu = np.empty(self.n_nlp), np.empty(self.n_nlp)
+        _check(load_library().qlnlp_variable_bounds(self._h, _np_ptr(xl), _np_ptr(xu)))
+        return xl, xu
+
+    @staticmethod
+    def _x(x, n) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.shape != (n,):
+            raise ValueError(f"x must have {n} entries")
+        return x
+
+    @staticmethod
+    def _out(a, n, name) -> np.ndarray:
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.size == n):
+            raise ValueError(f"{name} must be a contiguous float64 array with {n} entries (written in place)")
+        return a
+
+    def eval_objective(self, x) -> float:
+        f = np.empty(1)
+        _check(load_library().qlnlp_eval_objective(self._h, _np_ptr(self._x(x, self.n_nlp)), _np_ptr(f)))
+        return float(f[0])
+
+    def eval_objective_gradient(self, grad_f: np.ndarray, x) -> None:
+        self._out(grad_f, self.n_nlp, "grad_f")
+        _check(load_library().qlnlp_eval_objective_gradient(self._h, _np_ptr(self._x(x, self.n_nlp)), _np_ptr(grad_f)))
+
+    def eval_constraint(self, g: np.ndarray, x) -> None:
+        self._out(g, self.m_nlp, "g")
+        _check(load_library().qlnlp_eval_constraint(self._h, _np_ptr(self._x(x, self.n_nlp)), _np_ptr(g)))
+
+    def eval_constraint_jacobian(self, vec: np.ndarray, x) -> None:
+        self._out(vec, self.nnz, "vec")
+        _check(load_library().qlnlp_eval_constraint_jacobian(self._h, _np_ptr(self._x(x, self.n_nlp)), _np_ptr(vec)))
+
+    # ---- batched evaluation
+    def eval_batch(self, Z, *, x0=None, xf=None, want: Sequence[str] = ("f", "grad", "g", "jac"),
+                   out: Optional[Dict[str, "object"]] = None, stream=None) -> Dict[str, "object"]:
+        """Evaluate ``B`` decision vectors held in a CUDA tensor ``Z[B, ldz>=n_nlp]`` (fp64, row-major).
+
+        Returns device tensors ``f[B]``, ``grad[B, n_nlp]``, ``g[B, m_nlp]``, ``jac[B, nnz_block]`` (views of
+        buffers whose rows are padded to an even length so every row is 16-byte aligned).  The launch is
+        enqueued on the current torch stream and NOT synchronised.
+        """
+        import torch
+
+        if not (isinstance(Z, torch.Tensor) and Z.is_cuda and Z.dtype == torch.float64 and Z.dim() == 2):
+            raise ValueError("Z must be a 2-D float64 CUDA tensor")
+        if Z.stride(1) != 1 or Z.shape[1] != self.n_nlp:
+            raise ValueError(f"Z must be [B, {self.n_nlp}] with unit inner stride")
+        if Z.device.index != self.device:
+            raise ValueError(f"Z lives on cuda:{Z.device.index}, the evaluator on cuda:{self.device}")
+        B = Z.shape[0]
+        out = {} if out is None else out
+        dev = Z.device
+
+        def buf(name, width):
+            t = out.get(name)
+            if t is None:
+                t = torch.empty((B, even_ld(width)), dtype=torch.float64, device=dev)[:, :width]
+                out[name] = t
+            if not (t.is_cuda and t.dtype == torch.float64 and t.shape == (B, width) and t.stride(1) == 1):
+                raise ValueError(f"out[{name!r}] must be a float64 CUDA tensor of shape ({B}, {width})")
+            return t
+
+        io = _BatchIO()
+        io.Z, io.ldz = Z.data_ptr(), Z.stride(0) if B > 1 else self.n_nlp
+        for name, arr in (("x0", x0), ("xf", xf)):
+            if arr is not None:
+                if not (arr.is_cuda and arr.dtype == torch.float64 and arr.shape == (B, NX) and arr.is_contiguous()):
+                    raise ValueError(f"{name} must be a contiguous float64 CUDA tensor [B, 15]")
+                setattr(io, name, arr.data_ptr())
+        if "f" in want:
+            if out.get("f") is None:
+                out["f"] = torch.empty(B, dtype=torch.float64, device=dev)
+            io.f = out["f"].data_ptr()
+        if "grad" in want:
+            t = buf("grad", self.n_nlp)
+            io.grad, io.ldgrad = t.data_ptr(), t.stride(0) if B > 1 else self.n_nlp
+        if "g" in want:
+            t = buf("g", self.m_nlp)
+            io.g, io.ldg = t.data_ptr(), t.stride(0) if B > 1 else self.m_nlp
+        if "jac" in want:
+            t = buf("jac", self.nnz_block)
+            io.jac, io.ldjac = t.data_ptr(), t.stride(0) if B > 1 else even_ld(self.nnz_block)
+        s = torch.cuda.current_stream(dev) if stream is None else stream
+        _check(load_library().qlnlp_eval_batch_device(self._h, B, C.byref(io), C.c_void_p(s.cuda_stream)))
+        return out
+
+    def eval_batch_host(self, Z: np.ndarray, *, x0: Optional[np.ndarray] = None, xf: Optional[np.ndarray] = None,
+                        want: Sequence[str] = ("f", "grad", "g", "jac"),
+                        out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """Same evaluation on HOST arrays: H2D copy of Z, one fused launch per chunk, D2H copy of the outputs.
+
+        ``Z`` is ``[B, n_nlp]`` float64 (numpy; pinned memory makes the copies asynchronous).  Returns
+        numpy arrays; pass ``out`` to reuse (pinned) buffers.
+        """
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        if Z.ndim != 2 or Z.shape[1] != self.n_nlp:
+            raise ValueError(f"Z must be [B, {self.n_nlp}]")
+        B = Z.shape[0]
+        out = {} if out is None else out
+        io = _BatchIO()
+        io.Z, io.ldz = Z.ctypes.data, self.n_nlp
+        keep = [Z]
+        for name, arr in (("x0", x0), ("xf", xf)):
+            if arr is not None:
+                arr = np.ascontiguousarray(arr, dtype=np.float64)
+                if arr.shape != (B, NX):
+                    raise ValueError(f"{name} must be [B, 15]")
+                keep.append(arr)
+                setattr(io, name, arr.ctypes.data)
+        widths = {"f": None, "grad": self.n_nlp, "g": self.m_nlp, "jac": self.nnz_block}
+        for name in want:
+            w = widths[name]
+            shape = (B,) if w is None else (B, w)
+            a = out.get(name)
+            if a is None:
+                a = np.empty(shape)
+                out[name] = a
+            if not (a.dtype == np.float64 and a.shape == shape and a.flags.c_contiguous):
+                raise ValueError(f"out[{name!r}] must be contiguous float64 of shape {shape}")
+            setattr(io, name, a.ctypes.data)
+            if w is not None:
+                setattr(io, "ld" + name, w)
+        _check(load_library().qlnlp_eval_batch_host(self._h, B, C.byref(io)))
+        return out
+
+    def launch_info(self) -> Dict[str, int]:
+        info = (C.c_int64 * 5)()
+        _check(load_library().qlnlp_launch_info(self._h, info))
+        return dict(zip(("blocks", "threads_per_block", "smem_bytes", "blocks_per_sm", "sm_count"), list(info)))
+
+    def _debug_segments(self) -> np.ndarray:
+        n = C.c_int64()
+        L = load_library()
+        _check(L.qlnlp_debug_segments(self._h, None, 0, C.byref(n)))
+        segs = np.empty((n.value, 6), dtype=np.int64)
+        _check(L.qlnlp_debug_segments(self._h, _np_ptr(segs), n.value, C.byref(n)))
+        return segs

@@ -1,0 +1,79 @@
+// CPU emulation of the kernel's Jacobian value stream, built from the SAME headers the kernel
+// uses (layout.h: run offsets, constants, positions; rk4_dual_gen.h: RK4 duals + patch code),
+// following the kernel's segment plan: zero image -> run constants -> patch -> copy [start,end).
+// tests/test_layout_cpu.py compares the result with the oracle entry by entry, which checks all
+// of the kernel's index arithmetic without a GPU.  TEST HARNESS ONLY.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#define QL_ADD(a, b) ((a) + (b))
+#define QL_SUB(a, b) ((a) - (b))
+#define QL_MUL(a, b) ((a) * (b))
+#define QL_DIV(a, b) ((a) / (b))
+#define QL_FN static inline
+#define QL_ST(ptr, off, val) ((ptr)[(off)] = (val))
+#include "../../quadruped_landing_b200/csrc/layout.h"
+#include "../../quadruped_landing_b200/csrc/rk4_dual_gen.h"
+
+extern "C" {
+
+// segs: [nseg][6] = k0 nk start end tmpl buf (from qlnlp_debug_segments).  Returns 0, or a
+// negative code if the plan itself is inconsistent.
+int emul_jac_stream(int N, int k_trans, int init_mode, double g, double mb, double mf, double lb,
+                    const long long* segs, int nseg, const double* Z, double* out, int persist_templates)
+{
+    QlClass c;
+    ql_class_init(&c, N, k_trans, init_mode, g, mb, mf, lb);
+    std::vector<double> bufs[2] = {std::vector<double>(QL_JBUF, NAN), std::vector<double>(QL_JBUF, NAN)};
+    int tmpl[2] = {-1, -1};
+    for (int rep = 0; rep < (persist_templates ? 2 : 1); ++rep) {   // 2nd repetition reuses the images
+        for (int i = 0; i < c.nnz; ++i) out[i] = NAN;
+        for (int s = 0; s < nseg; ++s) {
+            const long long* sg = segs + 6 * s;
+            const int k0 = (int)sg[0], nk = (int)sg[1], start = (int)sg[2], end = (int)sg[3], tm = (int)sg[4], bi = (int)sg[5];
+            if (bi < 0 || bi > 1 || nk < 1 || nk > 2) return -1;
+            const int base = start & ~1;
+            if (end - base > QL_JBUF) return -2;
+            double* buf = bufs[bi].data();
+            if (tmpl[bi] != tm) {
+                std::memset(buf, 0, sizeof(double) * QL_JBUF);
+                for (int k = k0; k < k0 + nk; ++k) ql_write_run_constants(c, k, buf + (ql_run_off(c, k) - base));
+                tmpl[bi] = tm;
+            }
+            for (int k = k0; k < k0 + nk; ++k) {
+                double* run = buf + (ql_run_off(c, k) - base);
+                const double* x = Z + 20 * (k - 1);
+                if (k < N) {
+                    const double* u = x + 15;
+                    double xn[15], jv[QL_NJ_MODE1];
+                    double* p[7];
+                    for (int grp = 0; grp < 7; ++grp) p[grp] = run + ql_group_shift(c, k, grp);
+                    const bool jump = (k == k_trans - 1);
+                    if (k >= k_trans) { ql_rk4_jac_mode3(x, u, c.g, c.mb, c.mf, c.Ib, xn, jv); ql_patch_mode3(jv, p, jump); }
+                    else if (init_mode == 1) { ql_rk4_jac_mode1(x, u, c.g, c.mb, c.mf, c.Ib, xn, jv); ql_patch_mode1(jv, p, jump); }
+                    else { ql_rk4_jac_mode2(x, u, c.g, c.mb, c.mf, c.Ib, xn, jv); ql_patch_mode2(jv, p, jump); }
+                }
+                const double th = x[2];
+                run[ql_theta_pos(c, k)] = (th > 0) ? (-c.half_lb) * std::cos(th) : c.half_lb * std::cos(th);
+            }
+            for (int i = start; i < end; ++i) out[i] = buf[i - base];
+        }
+    }
+    return 0;
+}
+
+// closed-form helpers exposed for direct checks
+int emul_run_off(int N, int k_trans, int init_mode, int k)
+{
+    QlClass c;
+    ql_class_init(&c, N, k_trans, init_mode, -9.81, 10, 0.1, 0.5);
+    return ql_run_off(c, k);
+}
+int emul_rk4_pos(int N, int k_trans, int init_mode, int k, int i, int j)
+{
+    QlClass c;
+    ql_class_init(&c, N, k_trans, init_mode, -9.81, 10, 0.1, 0.5);
+    return ql_rk4_pos(c, k, i, j);
+}
+}

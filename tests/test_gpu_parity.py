@@ -1,0 +1,170 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): |a - b| <= 1e-14 + 1e-12 |b| in fp64; structure bit-exact.
+g, grad and the Jacobian values are in fact expected to be BIT-IDENTICAL (same operation order, no FMA);
+only f differs in summation order (warp tree vs sequential).
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_parity, perturbed_batch
+from oracle.oracle import Oracle
+import quadruped_landing_b200 as ql
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dflt():
+    p = ql.default_problem()
+    return p, ql.HybridNLP.from_problem(p), Oracle(p)
+
+
+def _bases(p, golden):
+    return [ql.initial_guess(p)] + [golden[f"data_{i}"] for i in range(1, 7)]
+
+
+def _dev_eval(nlp, Z, **kw):
+    Zd = torch.from_numpy(Z).cuda()
+    kw = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    out = nlp.eval_batch(Zd, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def test_known_answers_through_the_gpu(dflt, golden):
+    p, nlp, o = dflt
+    z = golden["data_6"]
+    # main.ipynb:710,712 (the same pins tests/test_oracle_kat.py holds for the oracle)
+    f = nlp.eval_objective(z)
+    assert abs(f - 1.1608112892558562e+02) <= 1e-12 * 116.1
+    g = np.empty(nlp.m_nlp)
+    nlp.eval_constraint(g, z)
+    assert np.abs(g[:1032]).max() == 1.4928675395736724e-06
+    assert np.array_equal(g, o.eval_c(z))
+    grad = np.empty(nlp.n_nlp)
+    nlp.eval_objective_gradient(grad, z)
+    assert np.array_equal(grad, o.grad_f(z))
+    vals = np.empty(nlp.nnz)
+    nlp.eval_constraint_jacobian(vals, z)
+    assert np.array_equal(vals, o.jac_c_sparse(z))
+
+
+def test_c2_batch_4096_against_oracle(dflt, golden):
+    """B=4096, Z_b = base[b mod 7] + 1e-2 xi_b, seed 4096, checked entry by entry."""
+    p, nlp, o = dflt
+    Z = perturbed_batch(p, _bases(p, golden), 4096, 1e-2, 4096)
+    got = _dev_eval(nlp, Z)
+    ref = o.eval_batch(Z)
+    assert_parity(got["f"], ref["f"], "f")
+    assert_parity(got["grad"], ref["grad"], "grad")
+    assert_parity(got["g"], ref["g"], "g")
+    assert_parity(got["jac"], ref["jac"], "jac")
+    # stronger than the stated tolerance: same bits (zeros compare equal regardless of sign)
+    assert np.array_equal(got["g"], ref["g"])
+    assert np.array_equal(got["grad"], ref["grad"])
+    assert np.array_equal(got["jac"], ref["jac"])
+
+
+def test_unperturbed_bases_exact_cancellation(dflt, golden):
+    """At the reference trajectory the torque terms cancel exactly; parity must survive that."""
+    p, nlp, o = dflt
+    Z = np.stack(_bases(p, golden))
+    got = _dev_eval(nlp, Z)
+    ref = o.eval_batch(Z)
+    for k in ("grad", "g", "jac"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert_parity(got["f"], ref["f"], "f")
+
+
+@pytest.mark.parametrize("N,kt,im", [(31, 11, 1), (41, 14, 2), (61, 21, 2), (81, 27, 1), (101, 34, 2), (121, 41, 1),
+                                     (2, 1, 1), (3, 2, 2), (33, 33, 1), (33, 1, 2), (64, 32, 1), (65, 2, 2)])
+def test_other_horizons_and_schedules(N, kt, im):
+    """SURVEY.md 8d C4 classes (varying horizon / contact schedule) plus edge cases of the pass/segment logic."""
+    p = ql.build_problem(N=N, k_trans=kt, init_mode=im)
+    nlp, o = ql.HybridNLP.from_problem(p), Oracle(p)
+    base = ql.initial_guess(p) if kt > 1 else np.zeros(p.n_nlp)
+    Z = perturbed_batch(p, [base], 300, 1e-2, 7)
+    got = _dev_eval(nlp, Z)
+    ref = o.eval_batch(Z)
+    for k in ("grad", "g", "jac"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert_parity(got["f"], ref["f"], "f")
+
+
+def test_per_evaluation_boundary_states(dflt):
+    """every problem of a sweep has its own x0 (drop height / pitch)."""
+    p, nlp, o = dflt
+    B = 64
+    rng = np.random.default_rng(5)
+    x0 = np.stack([ql.default_states(p.model, h_drop=h, theta0_deg=t)[0]
+                   for h, t in zip(np.linspace(0.25, 3.0, B), np.linspace(-40, -5, B))])
+    xf = np.tile(p.xf, (B, 1)) + 1e-3 * rng.standard_normal((B, 15))
+    Z = perturbed_batch(p, [ql.initial_guess(p)], B, 1e-2, 11)
+    got = _dev_eval(nlp, Z, x0=x0, xf=xf)
+    ref = o.eval_batch(Z, x0=x0, xf=xf)
+    assert np.array_equal(got["g"], ref["g"]) and np.array_equal(got["jac"], ref["jac"])
+
+
+def test_host_pointer_batch_and_partial_outputs(dflt, golden):
+    p, nlp, o = dflt
+    Z = perturbed_batch(p, _bases(p, golden), 1300, 1e-2, 13)      # > 2 pipeline chunks, ragged tail
+    got = nlp.eval_batch_host(Z)
+    ref = o.eval_batch(Z)
+    for k in ("grad", "g", "jac"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert_parity(got["f"], ref["f"], "f")
+    only = nlp.eval_batch_host(Z[:5], want=("g",))
+    assert set(only) == {"g"} and np.array_equal(only["g"], ref["g"][:5])
+    only = nlp.eval_batch_host(Z[:5], want=("f", "grad"))
+    assert np.array_equal(only["grad"], ref["grad"][:5])
+
+
+def test_unaligned_jacobian_rows_take_the_plain_store_path(dflt, golden):
+    """nnz_block is odd: tightly packed rows are only 8-byte aligned, so the TMA path must not be used."""
+    p, nlp, o = dflt
+    Z = perturbed_batch(p, _bases(p, golden), 33, 1e-2, 17)
+    Zd = torch.from_numpy(Z).cuda()
+    jac = torch.empty((33, nlp.nnz_block), dtype=torch.float64, device="cuda")      # ld = 32161 (odd)
+    out = nlp.eval_batch(Zd, want=("jac",), out={"jac": jac})
+    torch.cuda.synchronize()
+    assert np.array_equal(out["jac"].cpu().numpy(), o.eval_batch(Z, want=("jac",))["jac"])
+
+
+def test_dense_mode_is_the_references_matrix(golden):
+    p = ql.default_problem()
+    nlp = ql.HybridNLP.from_problem(p, use_sparse_jacobian=False)
+    o = Oracle(p)
+    z = golden["data_3"]
+    vec = np.full(nlp.nnz, np.nan)
+    nlp.eval_constraint_jacobian(vec, z)
+    jac = vec.reshape(nlp.n_nlp, nlp.m_nlp).T               # reshape(vec, m_nlp, n_nlp), moi.jl:20
+    assert np.array_equal(jac, o.jac_c_dense(z))
+
+
+def test_large_batch_properties():
+    """At full size (65,536 problems) the oracle is too slow to compare everything, so
+    check size-independent properties: constant entries of the value stream, rows that copy Z, and
+    position independence (a vector evaluates to the same bits wherever it sits in the batch)."""
+    p = ql.default_problem()
+    nlp, o = ql.HybridNLP.from_problem(p), Oracle(p)
+    B = 65536
+    small = perturbed_batch(p, [ql.initial_guess(p)], 256, 5e-2, 2 ** 20)
+    Zd = torch.from_numpy(small).cuda().repeat(B // 256, 1)
+    out = nlp.eval_batch(Zd)
+    torch.cuda.synchronize()
+    ref = o.eval_batch(small)
+    for k in ("grad", "g", "jac"):
+        t = out[k].view(B // 256, 256, -1)
+        assert bool((t == t[0:1]).all()), k                 # position independence
+        assert np.array_equal(t[0].cpu().numpy(), ref[k]), k
+    f = out["f"].view(B // 256, 256)
+    assert bool((f == f[0:1]).all())
+    g = out["g"]
+    assert bool((g[:, 929:990] == Zd[:, 4::20]).all())      # contact-first rows are y1_k
+    rows, cols = nlp.jacobian_structure_arrays()
+    const = np.nonzero((rows >= 30) & (rows <= 929) & (((rows - 30) // 15 + 1) * 20 < cols))[0]   # -I blocks
+    jc = out["jac"][:, torch.from_numpy(const).cuda()]
+    expect = torch.from_numpy(np.where((rows[const] - 30) % 15 == (cols[const] - 1) % 20, -1.0, 0.0)).cuda()
+    assert bool((jc == expect).all())

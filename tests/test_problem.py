@@ -1,0 +1,47 @@
+"""Host-side problem tables (quadruped_landing_b200/problem.py) against the oracle and the notebook."""
+import numpy as np
+
+from oracle import oracle
+import quadruped_landing_b200 as ql
+
+
+def test_lqr_cost_matches_oracle_bitwise():
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        Q, R = rng.uniform(0, 20, 15), rng.uniform(0, 1, 5)
+        xf, uf = rng.normal(size=15), rng.normal(size=5) * 50
+        c = ql.LQRCost(np.diag(Q), np.diag(R), xf, uf)
+        q0, r0, c0 = oracle.lqr_cost(Q, R, xf, uf)
+        assert np.array_equal(c.q, q0) and np.array_equal(c.r, r0) and c.c == c0
+
+
+def test_default_instance_values():
+    p = ql.default_problem()
+    # main.ipynb:92-93: v_init_y = sqrt(2*9.81*2) printed as 6.26418390534633
+    assert p.x0[8] == -6.26418390534633 and p.x0[2] == -30 * np.pi / 180 and p.x0[9] == -np.pi / 2
+    assert p.xf[1] == np.sqrt(0.25 ** 2 + 0.25 ** 2) and p.xf[0] == -0.25 and p.xf[5] == -0.5
+    assert (p.N, p.k_trans, p.init_mode) == (61, 21, 1)
+    # only two distinct stage-cost structs exist because Q[15] = 0
+    assert np.array_equal(p.r[0], p.r[19]) and np.array_equal(p.r[20], p.r[59]) and not np.array_equal(p.r[0], p.r[20])
+    assert p.R[60].max() == 0.0 and p.c[60] == ql.LQRCost(p.Q[60], p.R[60], p.xf).c
+
+
+def test_reference_trajectory_layout():
+    m = ql.PlanarQuadruped()
+    _, xt = ql.default_states(m)
+    for mode in (1, 2):
+        X, U = ql.reference_trajectory(m, 61, 21, xt, mode, 0.009)
+        assert len(X) == 61 and len(U) == 60
+        lead, other = (1, 3) if mode == 1 else (3, 1)
+        assert U[0][lead] == 98.10000000000001 and U[0][other] == 0.0 and U[0][4] == 0.001       # ref_traj.jl:24,35
+        assert U[20][1] == U[20][3] == 49.050000000000004 and U[20][4] == 0.02                     # ref_traj.jl:26-27,36
+        assert abs(X[60][14] - 0.54) < 1e-15 and np.array_equal(X[5][:14], xt[:14])
+
+
+def test_initial_guess_layout():
+    p = ql.default_problem()
+    z = ql.initial_guess(p)
+    X, U = ql.unpackZ(61, z)
+    assert np.array_equal(X[0][:14], p.x0[:14]) and np.allclose(X[20][:14], p.xf[:14], atol=1e-15)
+    assert abs(X[20][14] - 0.02) < 1e-15 and abs(X[60][14] - 0.82) < 1e-13        # 20*0.001 + 40*0.02
+    assert U[0][1] == 98.10000000000001

@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""Generates quadruped_landing_b200/csrc/rk4_dual_gen.h.
+
+What it does
+------------
+It symbolically executes the reference's RK4 step (src/planar_quadruped.jl:189-221
+over the three vector fields :36-185) on forward-mode dual numbers seeded like
+``ForwardDiff.jacobian(f, [x;u])`` (:225-248, one 20-wide chunk), with the dual
+arithmetic rules of ForwardDiff 0.10.25 (the same rules oracle/ql_oracle.c applies
+densely), but tracks which partials are STRUCTURALLY zero and drops every operation
+whose result is exactly determined without rounding:
+
+    x*0 -> 0      x*1 -> x      x+0 -> x      x-0 -> x      0-x -> -x
+    0/c -> 0      const (op) const -> folded in IEEE double by Python
+
+Every remaining operation is emitted in the reference's order with the reference's
+operand pairing, as explicit round-to-nearest add/mul/div (no FMA contraction).  The
+emitted straight-line code is therefore BIT-IDENTICAL to the dense dual evaluation
+for finite inputs (up to the sign of zero), while doing ~1/10 of the arithmetic and
+holding only the structurally non-zero Jacobian entries in registers.
+(tests/test_rk4_gen.py checks the bit-identity against the oracle on the CPU.)
+
+It also emits, per mode, the sparsity pattern of the 15x20 block and the code that
+patches those entries into a knot's run of the SPARSE_BLOCK value stream.
+
+Usage:  python tools/gen_rk4_dual.py            (rewrites the header in place)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "..", "quadruped_landing_b200", "csrc", "rk4_dual_gen.h")
+
+NX, NU, NP = 15, 5, 20
+
+
+class Graph:
+    """Hash-consed expression DAG over fp64 with exact-only simplifications."""
+
+    def __init__(self):
+        self.nodes = []          # id -> tuple
+        self.index = {}          # tuple -> id
+        self.zero = self.const(0.0)
+        self.one = self.const(1.0)
+
+    def _mk(self, key):
+        i = self.index.get(key)
+        if i is None:
+            i = len(self.nodes)
+            self.nodes.append(key)
+            self.index[key] = i
+        return i
+
+    def const(self, v):
+        v = float(v)
+        if v == 0.0:
+            v = 0.0  # collapse -0.0: the sign of zero is not part of parity
+        return self._mk(("c", v))
+
+    def inp(self, name):
+        return self._mk(("in", name))
+
+    def is_const(self, a):
+        return self.nodes[a][0] == "c"
+
+    def cval(self, a):
+        return self.nodes[a][1]
+
+    def add(self, a, b):
+        if self.is_const(a) and self.is_const(b):
+            return self.const(self.cval(a) + self.cval(b))
+        if a == self.zero:
+            return b
+        if b == self.zero:
+            return a
+        if a > b:
+            a, b = b, a  # IEEE add is commutative
+        return self._mk(("add", a, b))
+
+    def sub(self, a, b):
+        if self.is_const(a) and self.is_const(b):
+            return self.const(self.cval(a) - self.cval(b))
+        if b == self.zero:
+            return a
+        if a == self.zero:
+            return self.neg(b)
+        return self._mk(("sub", a, b))
+
+    def neg(self, a):
+        if self.is_const(a):
+            return self.const(-self.cval(a))
+        if self.nodes[a][0] == "neg":
+            return self.nodes[a][1]
+        return self._mk(("neg", a))
+
+    def mul(self, a, b):
+        if self.is_const(a) and self.is_const(b):
+            return self.const(self.cval(a) * self.cval(b))
+        if a == self.zero or b == self.zero:
+            return self.zero
+        if a == self.one:
+            return b
+        if b == self.one:
+            return a
+        if self.is_const(a) and self.cval(a) == -1.0:
+            return self.neg(b)
+        if self.is_const(b) and self.cval(b) == -1.0:
+            return self.neg(a)
+        if a > b:
+            a, b = b, a  # IEEE mul is commutative
+        return self._mk(("mul", a, b))
+
+    def div(self, a, b):
+        if self.is_const(a) and self.is_const(b):
+            return self.const(self.cval(a) / self.cval(b))
+        if a == self.zero:
+            return self.zero
+        if b == self.one:
+            return a
+        return self._mk(("div", a, b))
+
+
+class Dual:
+    __slots__ = ("g", "v", "p")
+
+    def __init__(self, g, v, p=None):
+        self.g = g
+        self.v = v
+        self.p = {} if p is None else {j: n for j, n in p.items() if n != g.zero}
+
+    def part(self, j):
+        return self.p.get(j, self.g.zero)
+
+    def _keys(self, o):
+        return sorted(set(self.p) | set(o.p))
+
+    # ForwardDiff dual.jl / partials.jl rules -------------------------------------------
+    def add(self, o):
+        g = self.g
+        return Dual(g, g.add(self.v, o.v), {j: g.add(self.part(j), o.part(j)) for j in self._keys(o)})
+
+    def sub(self, o):
+        g = self.g
+        return Dual(g, g.sub(self.v, o.v), {j: g.sub(self.part(j), o.part(j)) for j in self._keys(o)})
+
+    def mul(self, y):
+        # Dual(vx*vy, _mul_partials(px, py, vy, vx)):  (vy * px_i) + (vx * py_i)
+        g, x = self.g, self
+        return Dual(g, g.mul(x.v, y.v),
+                    {j: g.add(g.mul(y.v, x.part(j)), g.mul(x.v, y.part(j))) for j in x._keys(y)})
+
+    def neg(self):
+        g = self.g
+        return Dual(g, g.neg(self.v), {j: g.neg(n) for j, n in self.p.items()})
+
+    def divc(self, c):   # Dual / Real
+        g = self.g
+        return Dual(g, g.div(self.v, c), {j: g.div(n, c) for j, n in self.p.items()})
+
+    def addc(self, c):   # Dual + Real
+        return Dual(self.g, self.g.add(self.v, c), dict(self.p))
+
+    def mulc(self, c):   # Real * Dual
+        g = self.g
+        return Dual(g, g.mul(c, self.v), {j: g.mul(n, c) for j, n in self.p.items()})
+
+
+def contact_dynamics(g, mode, x, u, P):
+    """planar_quadruped.jl:36-79 / :89-132 / :142-185 on Duals (x: 14, u: 5)."""
+    zero = Dual(g, g.zero)
+    xb, yb = x[0], x[1]
+    x1, y1 = x[3], x[4]
+    x2, y2 = x[5], x[6]
+    F1x, F1y, F2x, F2y = u[0], u[1], u[2], u[3]
+    bax = F1x.add(F2x).divc(P["mb"])
+    bay = F1y.add(F2y).divc(P["mb"]).addc(P["g"])
+    t1 = F1x.neg().mul(y1.sub(yb))
+    t2 = F1y.mul(x1.sub(xb))
+    t3 = F2x.mul(y2.sub(yb))
+    t4 = F2y.mul(x2.sub(xb))
+    tau = t1.add(t2).sub(t3).add(t4)
+    bw = tau.divc(P["Ib"])
+    xd = [None] * 14
+    xd[0], xd[1], xd[2] = x[7], x[8], x[9]
+    xd[7], xd[8], xd[9] = bax, bay, bw
+    if mode == 1:
+        xd[3] = xd[4] = zero
+        xd[5], xd[6] = x[12], x[13]
+        xd[10] = xd[11] = zero
+        xd[12] = F2x.neg().divc(P["mf"])
+        xd[13] = F2y.neg().divc(P["mf"]).addc(P["g"])
+    elif mode == 2:
+        xd[3], xd[4] = x[10], x[11]
+        xd[5] = xd[6] = zero
+        xd[10] = F1x.neg().divc(P["mf"])
+        xd[11] = F1y.neg().divc(P["mf"]).addc(P["g"])
+        xd[12] = xd[13] = zero
+    else:
+        for i in (3, 4, 5, 6, 10, 11, 12, 13):
+            xd[i] = zero
+    return xd
+
+
+def rk4(g, mode, x, u, P):
+    """planar_quadruped.jl:189-221 on Duals (x: 15, u: 5)."""
+    h = u[4]
+    half, two, six = g.const(0.5), g.const(2.0), g.const(6.0)
+    f1 = contact_dynamics(g, mode, x[:14], u, P)
+    hh = h.mulc(half)
+    f2 = contact_dynamics(g, mode, [x[i].add(hh.mul(f1[i])) for i in range(14)], u, P)
+    f3 = contact_dynamics(g, mode, [x[i].add(hh.mul(f2[i])) for i in range(14)], u, P)
+    f4 = contact_dynamics(g, mode, [x[i].add(h.mul(f3[i])) for i in range(14)], u, P)
+    h6 = h.divc(six)
+    xn = []
+    for i in range(14):
+        s = f1[i].add(f2[i].mulc(two)).add(f3[i].mulc(two)).add(f4[i])
+        xn.append(x[i].add(h6.mul(s)))
+    xn.append(x[14].add(u[4]))
+    return xn
+
+
+def build(mode, with_partials):
+    g = Graph()
+    P = {n: g.inp(n) for n in ("g", "mb", "mf", "Ib")}
+    z = []
+    for j in range(NP):
+        name = f"x[{j}]" if j < NX else f"u[{j - NX}]"
+        z.append(Dual(g, g.inp(name), {j: g.one} if with_partials else None))
+    xn = rk4(g, mode, z[:NX], z[NX:], P)
+    return g, xn
+
+
+# -------------------------------------------------------------------------------- emission
+def emit_body(g, outputs, indent="    "):
+    """outputs: list of (lhs_string, node).  Returns (lines, op_counts)."""
+    live = set()
+    stack = [n for _, n in outputs]
+    while stack:
+        n = stack.pop()
+        if n in live:
+            continue
+        live.add(n)
+        key = g.nodes[n]
+        if key[0] in ("add", "sub", "mul", "div"):
+            stack.extend(key[1:3])
+        elif key[0] == "neg":
+            stack.append(key[1])
+    counts = {"add": 0, "sub": 0, "mul": 0, "div": 0, "neg": 0}
+
+    def ref(n):
+        key = g.nodes[n]
+        if key[0] == "c":
+            return repr(key[1])
+        if key[0] == "in":
+            return key[1]
+        return f"t{n}"
+
+    lines = []
+    for n in sorted(live):
+        key = g.nodes[n]
+        op = key[0]
+        if op in ("c", "in"):
+            continue
+        counts[op] += 1
+        if op == "neg":
+            lines.append(f"{indent}const double t{n} = -{ref(key[1])};")
+        else:
+            mac = {"add": "QL_ADD", "sub": "QL_SUB", "mul": "QL_MUL", "div": "QL_DIV"}[op]
+            lines.append(f"{indent}const double t{n} = {mac}({ref(key[1])}, {ref(key[2])});")
+    for lhs, n in outputs:
+        lines.append(f"{indent}{lhs} = {ref(n)};")
+    return lines, counts
+
+
+def pattern_of(g, xn):
+    """Column-major list of (i, j) whose partial is not structurally zero."""
+    pat = []
+    for j in range(NP):
+        for i in range(NX):
+            if xn[i].part(j) != g.zero:
+                pat.append((i, j))
+    return pat
+
+
+# column groups of a knot's run (see layout.h): pointer index used by the patch code
+def col_group(j):
+    if j <= 1:
+        return 0
+    if j == 2:
+        return 1
+    if j <= 4:
+        return 2
+    if j <= 6:
+        return 3
+    if j <= 16:
+        return 4
+    if j <= 18:
+        return 5
+    return 6
+
+
+def rk4_offset(i, j):
+    """Offset (in doubles, before the group shift) of RK4-block entry (i, j) inside a knot's run."""
+    if j < NX:
+        return 30 * j + 15 + i
+    return 450 + 15 * (j - NX) + i
+
+
+def main():
+    out = []
+    w = out.append
+    w("// GENERATED by tools/gen_rk4_dual.py -- do not edit by hand.")
+    w("//")
+    w("// Straight-line fp64 code for one RK4 step of the hybrid planar-quadruped dynamics")
+    w("// (reference: src/planar_quadruped.jl:36-221) and for the structurally non-zero entries")
+    w("// of its 15x20 Jacobian w.r.t. [x;u] (reference: ForwardDiff.jacobian, :225-248).")
+    w("// Operation order and operand pairing follow the reference / ForwardDiff 0.10.25 dual")
+    w("// rules exactly; operations whose result is exact (x*0, x*1, x+0, ...) are removed, so")
+    w("// the results are bit-identical to the dense 20-wide dual evaluation for finite inputs.")
+    w("//")
+    w("// The includer defines QL_ADD/QL_SUB/QL_MUL/QL_DIV (round-to-nearest, NO fma contraction),")
+    w("// QL_FN (function qualifiers) and QL_ST(ptr, off, val) (store of one double).")
+    w("#pragma once")
+    w("")
+    summary = []
+    for mode in (1, 2, 3):
+        # primal only
+        g, xn = build(mode, False)
+        lines, cnt = emit_body(g, [(f"xn[{i}]", xn[i].v) for i in range(NX)])
+        w(f"// mode {mode}, values only: {cnt}")
+        w(f"QL_FN void ql_rk4_mode{mode}(const double* x, const double* u, double g, double mb, double mf, double Ib,")
+        w(f"                           double* xn)")
+        w("{")
+        out.extend(lines)
+        w("}")
+        w("")
+        summary.append((mode, "primal", cnt))
+        # with partials
+        g, xn = build(mode, True)
+        pat = pattern_of(g, xn)
+        outs = [(f"xn[{i}]", xn[i].v) for i in range(NX)]
+        outs += [(f"jv[{n}]", xn[i].part(j)) for n, (i, j) in enumerate(pat)]
+        lines, cnt = emit_body(g, outs)
+        nconst = sum(1 for (i, j) in pat if g.is_const(xn[i].part(j)))
+        w(f"// mode {mode}, values + Jacobian pattern ({len(pat)} entries, {nconst} of them constants): {cnt}")
+        w(f"#define QL_NJ_MODE{mode} {len(pat)}")
+        w(f"QL_FN void ql_rk4_jac_mode{mode}(const double* x, const double* u, double g, double mb, double mf, double Ib,")
+        w(f"                               double* xn, double* jv)")
+        w("{")
+        out.extend(lines)
+        w("}")
+        w("")
+        w(f"// pattern of mode {mode}: jv[n] = d xn[PAT_I[n]] / d z[PAT_J[n]], column-major order")
+        w(f"static const unsigned char QL_PAT_I_MODE{mode}[{len(pat)}] = {{{', '.join(str(i) for i, _ in pat)}}};")
+        w(f"static const unsigned char QL_PAT_J_MODE{mode}[{len(pat)}] = {{{', '.join(str(j) for _, j in pat)}}};")
+        w("")
+        w(f"// Patch jv[] into a knot's run.  p[grp] points at the run start shifted by the extras that")
+        w(f"// precede column group grp (layout.h: ql_col_group / ql_group_shift).  `jump` applies the")
+        w(f"// reference's jump Jacobian Diagonal([1,1,1,1,0,1,0,1,1,1,0,0,0,0,0]) (planar_quadruped.jl:262-263).")
+        w(f"template <typename PTR>")
+        w(f"QL_FN void ql_patch_mode{mode}(const double* jv, const PTR* p, bool jump)")
+        w("{")
+        keep = (1, 1, 1, 1, 0, 1, 0, 1, 1, 1, 0, 0, 0, 0, 0)
+        for n, (i, j) in enumerate(pat):
+            val = f"jv[{n}]" if keep[i] else f"(jump ? 0.0 : jv[{n}])"
+            w(f"    QL_ST(p[{col_group(j)}], {rk4_offset(i, j)}, {val});")
+        w("}")
+        w("")
+        summary.append((mode, "jac", cnt, len(pat)))
+    text = "\n".join(out) + "\n"
+    with open(OUT, "w") as f:
+        f.write(text)
+    for s in summary:
+        print(s, file=sys.stderr)
+    print("wrote", os.path.normpath(OUT), file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()
