@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: batched NLP evaluations per second (f + grad + g + sparse Jacobian).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference algorithm
+    torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU, weak scaling
+
+A step = one fused launch over one batch of B=4096 perturbed decision vectors of the reference's default
+landing NLP (N=61 knots, k_trans=21, init_mode=1; BASELINE.json configs[1]) per GPU,
+producing f, grad_f, g and the SPARSE_BLOCK Jacobian values (285,480 algorithmic bytes per evaluation).
+Rank 0 prints ONE JSON line.  The oracle (oracle/) is used here only as the timed CPU baseline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "batched NLP evals/s (g+sparse Jacobian)"
+UNIT = "evals/s"
+B_PER_GPU = 4096
+N_INPUT_SETS = 4            # 4 x 39.8 MB of decision vectors = 159 MB > 126 MB L2
+SEED = 4096
+SIGMA = 1e-2
+HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def workload_config(n_gpus, what):
+    return {
+        "workload": "C2: B=4096 perturbed decision vectors per GPU of the reference landing NLP "
+                    "(N=61, k_trans=21, init_mode=1), Z_b = base[b mod 7] + 1e-2*xi_b, seed 4096",
+        "outputs": what,
+        "jacobian_pattern": "SPARSE_BLOCK (32161 values/eval, reference column-major order)",
+        "batch_per_gpu": B_PER_GPU,
+        "global_batch": B_PER_GPU * n_gpus,
+        "bytes_per_eval": 285480,
+        "l2": f"inputs rotate over {N_INPUT_SETS} distinct batches (159 MB > 126 MB L2); every step also writes 1.17 GB",
+        "parallelism": f"batch sharded over {n_gpus} GPU(s), no collective on the hot path",
+    }
+
+
+def make_inputs(prob, rank, nsets):
+    """Synthetic C2 batches: bases = initial guess + the six shipped solutions."""
+    import quadruped_landing_b200 as ql
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_solutions.npz"))
+    bases = [ql.initial_guess(prob)] + [g[f"data_{i}"] for i in range(1, 7)]
+    out = []
+    for s in range(nsets):
+        rng = np.random.default_rng(SEED + 1000 * rank + s)
+        Z = np.stack([bases[b % 7] for b in range(B_PER_GPU)]) + SIGMA * rng.standard_normal((B_PER_GPU, prob.n_nlp))
+        Z[:, 19::20] = np.clip(Z[:, 19::20], 1e-3, 2e-2)
+        out.append(np.ascontiguousarray(Z))
+    return out
+
+
+class ClockSampler:
+    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+
+    def __init__(self, index, uuid=None):
+        self.samples, self.reasons, self._stop = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _once(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        for bit, name in names.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._once()
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self.t.start()
+
+    def stop(self):
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        try:
+            self._once()          # at least one sample while work is still queued / just finished
+        except Exception:
+            pass
+        self._stop.set()
+        self.t.join(timeout=1)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class CpuRunner:
+    """The CPU restatement (oracle port) on the host cores: all four outputs, SPARSE_BLOCK Jacobian.
+    Buffers are allocated and first-touched once; step() times one pass over the sample."""
+
+    def __init__(self, prob, Z, nthreads):
+        from oracle import oracle as om
+        self.o = om.Oracle(prob)
+        o, n = self.o, Z.shape[0]
+        self.n = n
+        self.bufs = (np.empty(n), np.empty((n, o.n_nlp)), np.empty((n, o.m_nlp)), np.empty((n, o.nnz)))
+        f, grad, g, jac = self.bufs
+        self.Z = Z
+        self.L = om.lib()
+        self.args = (o.plan, o._p, n, om._ptr(Z), o.n_nlp, None, None, om._ptr(f), om._ptr(grad), o.n_nlp,
+                     om._ptr(g), o.m_nlp, om._ptr(jac), o.nnz, int(nthreads))
+        self.L.qlo_eval_batch(*self.args)              # first touch of the output pages
+
+    def step(self):
+        t0 = time.perf_counter()
+        self.L.qlo_eval_batch(*self.args)
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores.  Julia is not installed in the image
+    (DESIGN.md), so this is the C restatement in oracle/ (kind "port") with OpenMP over the batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import quadruped_landing_b200 as ql
+    from oracle.oracle import Oracle
+    prob = ql.default_problem()
+    Z = make_inputs(prob, 0, 1)[0]
+    cores = Oracle.max_threads()
+    sample = 1024 if cores < 32 else B_PER_GPU          # bounded: a few seconds per step on any box
+    Zs = Z[:sample]
+    runner = CpuRunner(prob, Zs, cores)
+    for _ in range(max(0, min(args.warmup, 2))):
+        runner.step()
+    times = []
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        times.append(runner.step())
+        if time.perf_counter() - t_all > 150:            # keep the whole run within minutes
+            break
+    vals = times
+    value = sample * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * sample / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, "f, grad_f, g, SPARSE_BLOCK Jacobian values"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} of the {B_PER_GPU} decision vectors of the same batch per step, "
+                                   "OpenMP static schedule over the batch, outputs written to host memory"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of the reference algorithm (dense 20-wide forward-mode duals per knot), not Julia: "
+                "no julia binary exists in the image.  The only recorded Julia figure is ~23 evals/s, 1 thread "
+                "(src/main.ipynb:717-725).",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import quadruped_landing_b200 as ql
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the framework has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    prob = ql.default_problem()
+    nlp = ql.HybridNLP.from_problem(prob, device=local)
+    host_sets = make_inputs(prob, rank, N_INPUT_SETS)
+    Zs = [torch.from_numpy(z).to(dev) for z in host_sets]
+    want = ("f", "grad", "g", "jac")
+    out = nlp.eval_batch(Zs[0], want=want)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -------------------------------------------------------
+    # warm-up: W steps as asked, and keep going until ~0.5 s of load so SM clocks have ramped up
+    t0 = time.perf_counter()
+    i = 0
+    while i < max(args.warmup, 3) or time.perf_counter() - t0 < args.min_warmup_s:
+        nlp.eval_batch(Zs[i % N_INPUT_SETS], want=want, out=out)
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    extra_warmup = i
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None))
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        nlp.eval_batch(Zs[s % N_INPUT_SETS], want=want, out=out)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = B_PER_GPU * n_gpus / (ms_step * 1e-3)
+
+    # the headline metric names "g + sparse Jacobian": also time that subset (not the reported value)
+    for _ in range(3):
+        nlp.eval_batch(Zs[0], want=("g", "jac"), out=out)
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        nlp.eval_batch(Zs[s % N_INPUT_SETS], want=("g", "jac"), out=out)
+    e1.record()
+    barrier()
+    ms_gj = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
+    pin = [torch.from_numpy(z).pin_memory() for z in host_sets[:2]]
+    hout = {"f": torch.empty(B_PER_GPU, dtype=torch.float64).pin_memory(),
+            "grad": torch.empty((B_PER_GPU, nlp.n_nlp), dtype=torch.float64).pin_memory(),
+            "g": torch.empty((B_PER_GPU, nlp.m_nlp), dtype=torch.float64).pin_memory(),
+            "jac": torch.empty((B_PER_GPU, nlp.nnz_block), dtype=torch.float64).pin_memory()}
+    hnp = {k: v.numpy() for k, v in hout.items()}
+    e2e_steps = max(2, min(args.steps, 20))
+    for s in range(2):
+        nlp.eval_batch_host(pin[s % 2].numpy(), want=want, out=hnp)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        nlp.eval_batch_host(pin[s % 2].numpy(), want=want, out=hnp)
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = B_PER_GPU * n_gpus * e2e_steps / t_e2e
+    h2d = B_PER_GPU * nlp.n_nlp * 8
+    d2h = B_PER_GPU * (1 + nlp.n_nlp + nlp.m_nlp + nlp.nnz_block) * 8
+
+    # ---- optional final gather of per-problem scalars over NCCL (outside every timed region)
+    if world > 1:
+        parts = [torch.empty_like(out["f"]) for _ in range(world)]
+        dist.all_gather(parts, out["f"])
+        torch.cuda.synchronize()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bytes_per_launch = 285480 * B_PER_GPU
+        achieved = bytes_per_launch / (ms_step * 1e-3) / 1e9          # GB/s per GPU (max-over-ranks time)
+        traffic = recorded_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(n_gpus, "f, grad_f, g, SPARSE_BLOCK Jacobian values (full evaluation)"),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "path": "qlnlp_eval_batch_host: pinned host buffers, 512-evaluation chunks "
+                                                 "pipelined over 2 streams; bound by PCIe D2H of 285 KB/eval"},
+            "gpu_launches": args.steps * n_gpus,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "kernel": "ql::eval_kernel<true>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "traffic_source": (traffic or {}).get("source")},
+            "g_jac_only": {"value": B_PER_GPU * n_gpus / (ms_gj * 1e-3), "ms_per_step": ms_gj,
+                           "GBps_per_gpu": 275752 * B_PER_GPU / (ms_gj * 1e-3) / 1e9},
+            "launch": nlp.launch_info(),
+            "warmup_steps_run": extra_warmup,
+        }
+        # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same batch
+        if n_gpus == 1 and not args.no_cpu:
+            from oracle.oracle import Oracle
+            cores = Oracle.max_threads()
+            sample = 1024 if cores < 32 else B_PER_GPU
+            runner = CpuRunner(prob, host_sets[0][:sample], cores)
+            v = sample / statistics.median([runner.step() for _ in range(3)])
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{sample} decision vectors of the same batch, 3 repetitions (median), "
+                                              "OpenMP over the batch on all host cores"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--min-warmup-s", type=float, default=0.5,
+                    help="keep warming up until this much load has run (SM clocks ramp from idle); 0 under ncu")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,7 +29,7 @@ class _Problem(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    """Compile the oracle with the committed Makefile (gcc -O2 -ffp-contract=off -fopenmp)."""
+    """Compile the oracle with the committed Makefile (gcc -O3 -ffp-contract=off -fopenmp)."""
     srcs = [os.path.join(_HERE, f) for f in ("ql_oracle.c", "ql_oracle.h", "ql_dyn_impl.inc", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:

@@ -2,7 +2,7 @@
  * ql_oracle.c -- CPU oracle (see ql_oracle.h for the status header).
  * TEST INFRASTRUCTURE ONLY: never linked into or called by the product path.
  *
- * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared (oracle/Makefile).
+ * Build: gcc -O3 -ffp-contract=off -fopenmp -fPIC -shared (oracle/Makefile).
  * Every function cites the reference lines (relative to /root/reference/src/) it restates.
  */
 #include "ql_oracle.h"
