@@ -28,6 +28,7 @@
 #define QL_LANES 32           // knots per pass: one lane per knot
 #define QL_ZSTRIDE 21         // padded knot stride of the staged decision vector (odd => conflict-free)
 #define QL_JBUF 1064          // doubles per J staging buffer: two runs (<= 529 + 531) + parity, rounded to 16 B
+#define QL_MAX_N 1024
 #define QL_NCOST 41           // cost fields per knot: Q[15] q[15] R[5] r[5] c
 
 struct QlClass {
@@ -137,13 +138,14 @@ QL_HD void ql_write_run_constants(const QlClass& c, int k, double* run)
 
 // ---- segments: what one bulk store moves ---------------------------------------------------
 // A segment is 1 or 2 consecutive knots of one pass.  Its image lives in a staging buffer at offset
-// (start & 1) so that shared and global addresses agree modulo 16 B.
+// (start & 1) so that shared and global addresses agree modulo 16 B.  16-byte records: the kernel
+// keeps the plan in shared memory and reads a segment with one 128-bit load.
 struct QlSeg {
-    int k0;        // first knot (1-based)
-    int nk;        // 1 or 2
-    int start;     // stream offset of knot k0's run
-    int end;       // stream offset one past the last knot's run
-    int tmpl;      // template id: equal ids <=> identical constant image
-    int buf;       // staging buffer 0/1
-    int pad0, pad1; // 32-byte records: the kernel reads a segment as two aligned int4
+    int start;            // stream offset of knot k0's run
+    int end;              // stream offset one past the last knot's run
+    short k0;             // first knot (1-based)
+    signed char nk;       // 1 or 2
+    signed char buf;      // staging buffer 0/1
+    short tmpl;           // template id: equal ids <=> identical constant image
+    short pad;
 };

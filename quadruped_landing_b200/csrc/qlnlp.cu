@@ -69,6 +69,8 @@ struct qlnlp_handle_s {
     int sm_count = 0;
     int blocks_per_sm[2] = {0, 0};     // [with_jac]
     size_t smem[2] = {0, 0};
+    double rmb = 0, rmf = 0, rIb = 0;  // reciprocals of the divisors
+    bool fastdiv = false;              // reciprocal-FMA division verified exact for this model
     int64_t last_launch[5] = {0, 0, 0, 0, 0};
     HostLane lanes[2];
     int64_t ldz_e = 0, ldgrad_e = 0, ldg_e = 0, ldjac_e = 0;   // even leading dimensions of the scratch
@@ -115,26 +117,53 @@ void plan_segments(const QlClass& c, std::vector<QlSeg>& segs, std::vector<int>&
         for (int k = ka; k <= kb; k += 2, ++idx) {
             QlSeg s;
             std::memset(&s, 0, sizeof s);
-            s.k0 = k;
-            s.nk = (k + 1 <= kb) ? 2 : 1;
+            const int nk = (k + 1 <= kb) ? 2 : 1;
+            s.k0 = (short)k;
+            s.nk = (signed char)nk;
             s.start = ql_run_off(c, k);
-            s.end = (k + s.nk > c.N) ? c.nnz : ql_run_off(c, k + s.nk);
-            std::vector<int> sig{s.start & 1, s.nk};
-            for (int q = k; q < k + s.nk; ++q) {
+            s.end = (k + nk > c.N) ? c.nnz : ql_run_off(c, k + nk);
+            // everything that determines the constant image of the segment
+            std::vector<int> sig{s.start & 1, nk};
+            for (int q = k; q < k + nk; ++q) {
                 sig.push_back(q == 1);
                 sig.push_back(q == c.N - 1);
                 sig.push_back(q == c.N);
                 sig.push_back(ql_e4(c, q));
                 sig.push_back(ql_e6(c, q));
+                sig.push_back(q >= c.k_trans);          // RK4 block constants of mode 3 vs the initial mode
+                sig.push_back(q == c.k_trans - 1);      // jump knot: masked rows hold 0 instead of 1
             }
             auto it = ids.find(sig);
             if (it == ids.end()) it = ids.emplace(sig, (int)ids.size()).first;
-            s.tmpl = it->second;
-            s.buf = (int)(segs.size() & 1);      // alternate over the whole evaluation
+            s.tmpl = (short)it->second;
+            s.buf = (signed char)(segs.size() & 1);      // alternate over the whole evaluation
             segs.push_back(s);
         }
         seg_begin.push_back((int)segs.size());
     }
+}
+
+// q = a*r; q' = fma(fma(-q, b, a), r, q) is the correctly rounded a/b for r = RN(1/b) (Markstein) unless b's
+// significand is all ones.  Verify per divisor on pseudo-random numerators; any miss disables the fast path.
+bool fastdiv_is_exact(double b)
+{
+    if (!(std::isfinite(b)) || b == 0.0) return false;
+    const double r = 1.0 / b;
+    unsigned long long s = 88172645463325252ULL;
+    for (int i = 0; i < 200000; ++i) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        const double m = 1.0 + (double)(s >> 12) * (1.0 / 4503599627370496.0);
+        const double a = std::ldexp((s & 1) ? -m : m, (int)((s >> 3) % 81) - 40);
+        const double q = a * r;
+        if (std::fma(std::fma(-q, b, a), r, q) != a / b) return false;
+    }
+    return true;
+}
+
+const void* kernel_fn(bool with_jac, bool fast)
+{
+    if (with_jac) return fast ? (const void*)ql::eval_kernel<true, true> : (const void*)ql::eval_kernel<true, false>;
+    return fast ? (const void*)ql::eval_kernel<false, true> : (const void*)ql::eval_kernel<false, false>;
 }
 
 int check_handle(qlnlp_handle h)
@@ -178,7 +207,7 @@ int ensure_device(qlnlp_handle h)
         if (h->smem[wj] > (size_t)prop.sharedMemPerBlockOptin)
             return fail(QLNLP_EINVAL, "N=%d needs %zu B of shared memory per warp (> %zu)", h->cls.N, h->smem[wj],
                         (size_t)prop.sharedMemPerBlockOptin);
-        const void* fn = wj ? (const void*)ql::eval_kernel<true> : (const void*)ql::eval_kernel<false>;
+        const void* fn = kernel_fn(wj != 0, h->fastdiv);
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[wj]));
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int nb = 0;
@@ -205,8 +234,10 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
 
     ql::Launch P;
     P.c = c;
+    P.rmb = h->rmb; P.rmf = h->rmf; P.rIb = h->rIb;
     P.cost = h->d_cost;
     P.npad = h->npad;
+    P.nseg = (int)h->segs.size();
     P.x0_def = h->d_x0xf;
     P.xf_def = h->d_x0xf + QL_NX;
     P.segs = h->d_segs;
@@ -223,9 +254,8 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     const int wj = io->jac ? 1 : 0;
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm[wj];
     const int grid = (int)std::min<int64_t>(B, resident);
-    if (wj) ql::eval_kernel<true><<<grid, QL_LANES, h->smem[wj], stream>>>(P);
-    else ql::eval_kernel<false><<<grid, QL_LANES, h->smem[wj], stream>>>(P);
-    CUDA_TRY(cudaGetLastError());
+    void* args[] = {&P};
+    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj != 0, h->fastdiv), dim3(grid), dim3(QL_LANES), args, h->smem[wj], stream));
     h->last_launch[0] = grid;
     h->last_launch[1] = QL_LANES;
     h->last_launch[2] = (int64_t)h->smem[wj];
@@ -328,7 +358,7 @@ int qlnlp_create(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_ha
 {
     if (!d || !out) return fail(QLNLP_EINVAL, "null argument");
     *out = nullptr;
-    if (d->N < 2 || d->N > 1024) return fail(QLNLP_EINVAL, "N=%lld outside [2, 1024]", (long long)d->N);
+    if (d->N < 2 || d->N > QL_MAX_N) return fail(QLNLP_EINVAL, "N=%lld outside [2, 1024]", (long long)d->N);
     if (d->k_trans < 1 || d->k_trans > d->N) return fail(QLNLP_EINVAL, "k_trans=%lld outside [1, N]", (long long)d->k_trans);
     if (d->init_mode != 1 && d->init_mode != 2) return fail(QLNLP_EINVAL, "init_mode must be 1 or 2");
     if (jac_mode != QLNLP_JAC_SPARSE_BLOCK && jac_mode != QLNLP_JAC_DENSE) return fail(QLNLP_EINVAL, "unknown jac_mode %d", jac_mode);
@@ -355,6 +385,11 @@ int qlnlp_create(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_ha
         h->cost[(size_t)40 * h->npad + k] = d->c[k];
     }
     plan_segments(h->cls, h->segs, h->seg_begin);
+    h->rmb = 1.0 / h->cls.mb;
+    h->rmf = 1.0 / h->cls.mf;
+    h->rIb = 1.0 / h->cls.Ib;
+    h->fastdiv = fastdiv_is_exact(h->cls.mb) && fastdiv_is_exact(h->cls.mf) && fastdiv_is_exact(h->cls.Ib) &&
+                 fastdiv_is_exact(6.0);
     *out = h;
     return QLNLP_OK;
 }

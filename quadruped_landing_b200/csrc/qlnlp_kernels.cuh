@@ -3,21 +3,25 @@
 // One warp per trajectory (decision vector), one lane per knot, ceil(N/32) passes; one warp per
 // CTA so warps never synchronise with each other.  Per evaluation the warp
 //   1. stages Z through shared memory (cp.async, coalesced 8-byte elements, knot stride padded
-//      to 21 doubles so the lane-per-knot reads are bank-conflict free),
+//      to 21 doubles so the lane-per-knot reads are bank-conflict free); the next decision vector is
+//      prefetched while the last pass streams its Jacobian values,
 //   2. evaluates, per lane, the quadratic stage cost + gradient (costs.jl:6-34), one RK4 step of
 //      the hybrid dynamics and its defect (constraints.jl:6-41), the contact / final-force /
-//      body-clearance rows (constraints.jl:48-113,154) and the structurally non-zero entries of
-//      the 15x20 RK4 Jacobian by forward-mode duals held in registers (rk4_dual_gen.h),
-//   3. writes g/grad through small shared staging tiles with coalesced stores, reduces the cost
-//      over the warp with shuffles,
+//      body-clearance rows (constraints.jl:48-113,154) and the value-dependent entries of the
+//      15x20 RK4 Jacobian by forward-mode duals held in registers (rk4_dual_gen.h),
+//   3. writes the gradient in place over its slice of the staged Z and flushes it with coalesced
+//      stores; reduces the cost over the warp with shuffles,
 //   4. streams the SPARSE_BLOCK Jacobian values: the value stream is a concatenation of per-knot
-//      runs (layout.h) that are >85 % structural constants, so each 1-2-knot segment lives in a
+//      runs (layout.h) that are ~90 % structural constants, so each 1-2-knot segment lives in a
 //      shared-memory image whose constants persist from one evaluation to the next; the owner
 //      lanes patch only the value-dependent entries and one lane fires a TMA bulk store
 //      (cp.async.bulk.global.shared::cta, SASS UBLKCP) of the whole 4-8 KB segment.
 // All arithmetic is fp64 with explicit round-to-nearest add/mul/div (no FMA contraction) in the
 // reference's operation order, so g, grad and the Jacobian values are bit-identical to the CPU
-// oracle; only the cost reduction order (warp tree vs. sequential) differs.
+// oracle (sin/cos aside); only the cost reduction order (warp tree vs. sequential) differs.
+// Divisions by the model constants use q = a*r, q' = fma(fma(-q, b, a), r, q) with r = RN(1/b), which is
+// the correctly rounded quotient (Markstein); the host verifies this per divisor at create time and falls
+// back to IEEE division (template parameter FASTDIV = false) otherwise.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -62,13 +66,34 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // make generic-proxy shared-memory writes visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// model constants + their reciprocals; division by a constant, correctly rounded
+template <bool FAST>
+struct Consts {
+    double g, mb, mf, Ib, rmb, rmf, rIb;
+    __device__ __forceinline__ static double div(double a, double b, double r)
+    {
+        if (FAST) {
+            const double q = __dmul_rn(a, r);
+            return __fma_rn(__fma_rn(-q, b, a), r, q);
+        }
+        return __ddiv_rn(a, b);
+    }
+    __device__ __forceinline__ double div_mb(double a) const { return div(a, mb, rmb); }
+    __device__ __forceinline__ double div_mf(double a) const { return div(a, mf, rmf); }
+    __device__ __forceinline__ double div_Ib(double a) const { return div(a, Ib, rIb); }
+    __device__ __forceinline__ double div_six(double a) const { return div(a, 6.0, 0.16666666666666666); }
+};
+
 }  // namespace ql
 
 // generated RK4 + Jacobian code: explicit rounding, shared-memory patch stores
 #define QL_ADD(a, b) __dadd_rn((a), (b))
 #define QL_SUB(a, b) __dsub_rn((a), (b))
 #define QL_MUL(a, b) __dmul_rn((a), (b))
-#define QL_DIV(a, b) __ddiv_rn((a), (b))
+#define QL_DIV_MB(a) K.div_mb(a)
+#define QL_DIV_MF(a) K.div_mf(a)
+#define QL_DIV_IB(a) K.div_Ib(a)
+#define QL_DIV_SIX(a) K.div_six(a)
 #define QL_FN __device__ __forceinline__
 #define QL_ST(ptr, off, val) ql::st_shared_f64((ptr) + 8u * (off), (val))
 #include "rk4_dual_gen.h"
@@ -79,8 +104,10 @@ namespace ql {
 
 struct Launch {
     QlClass c;
+    double rmb, rmf, rIb;      // RN(1/mb), RN(1/mf), RN(1/Ib)
     const double* cost;        // [QL_NCOST][npad] field-major: Q 0-14, q 15-29, R 30-34, r 35-39, c 40
     int npad;
+    int nseg;
     const double* x0_def;      // [15]  desc.x0
     const double* xf_def;      // [15]  desc.xf
     const QlSeg* segs;         // segment plan, all passes
@@ -96,13 +123,12 @@ struct Launch {
     int bulk;                  // 1: jac rows are 16 B aligned -> TMA bulk stores
 };
 
-// shared memory carve-up (doubles)
+// shared memory carve-up (doubles): staged Z | two J staging buffers | segment plan
 __host__ __device__ inline int zbuf_len(int N) { return (QL_ZSTRIDE * N + 1) & ~1; }
-constexpr int GD_LEN = QL_LANES * QL_NX;        // dynamics defects of one pass
-constexpr int GR_LEN = QL_LANES * QL_ZSTRIDE;   // gradient of one pass (knot stride padded to 21)
 __host__ __device__ inline size_t smem_bytes(int N, bool with_jac)
 {
-    return sizeof(double) * (size_t)(zbuf_len(N) + GD_LEN + GR_LEN + (with_jac ? 2 * QL_JBUF : 0));
+    const int nseg_max = (N + 1) / 2 + (N + QL_LANES - 1) / QL_LANES;
+    return sizeof(double) * (size_t)zbuf_len(N) + (with_jac ? sizeof(double) * 2 * QL_JBUF + sizeof(QlSeg) * nseg_max : 0);
 }
 
 // cp.async the decision vector into the padded shared layout (element e -> e + e/20)
@@ -112,26 +138,32 @@ __device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigne
     cp_async_commit();
 }
 
-template <bool WITH_JAC>
-__global__ void __launch_bounds__(QL_LANES) eval_kernel(const __grid_constant__ Launch P)
+template <bool WITH_JAC, bool FASTDIV>
+__global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant__ Launch P)
 {
     extern __shared__ __align__(16) double smem[];
     const QlClass& c = P.c;
     const int lane = threadIdx.x;
 
     double* const zbuf = smem;
-    double* const gd = zbuf + zbuf_len(c.N);
-    double* const gr = gd + GD_LEN;
-    double* const jb = gr + GR_LEN;
+    double* const jb = zbuf + zbuf_len(c.N);
+    QlSeg* const plan = reinterpret_cast<QlSeg*>(jb + 2 * QL_JBUF);
     const unsigned zaddr = smem_addr(zbuf);
     const unsigned jaddr = smem_addr(jb);
     int tmpl0 = -1, tmpl1 = -1;        // template currently held by staging buffer 0 / 1
 
-    const double mg = c.g, mb = c.mb, mf = c.mf, Ib = c.Ib;
+    Consts<FASTDIV> K;
+    K.g = c.g; K.mb = c.mb; K.mf = c.mf; K.Ib = c.Ib; K.rmb = P.rmb; K.rmf = P.rmf; K.rIb = P.rIb;
     const bool first_is_y1 = (c.init_mode == 1);    // contact-first reads y1 (mode 1) or y2 (mode 2)
 
     long long b = blockIdx.x;
     if (b < P.B) stage_z(P.Z + b * P.ldz, zaddr, c.n_nlp, lane);
+    if (WITH_JAC) {
+        // the segment plan lives in shared memory: one 16-byte record per segment
+        const int4* src = reinterpret_cast<const int4*>(P.segs);
+        int4* dst = reinterpret_cast<int4*>(plan);
+        for (int i = lane; i < P.nseg; i += QL_LANES) dst[i] = __ldg(src + i);
+    }
 
     for (; b < P.B; b += gridDim.x) {
         cp_async_wait_all();
@@ -139,72 +171,62 @@ __global__ void __launch_bounds__(QL_LANES) eval_kernel(const __grid_constant__ 
         double fsum = 0.0;
         double* const grow = P.g ? P.g + b * P.ldg : nullptr;
         double* const gradrow = P.grad ? P.grad + b * P.ldgrad : nullptr;
-        double* const jrow = WITH_JAC ? P.jac + b * P.ldjac : nullptr;
 
         for (int p = 0; p < c.npass; ++p) {
             const int k = p * QL_LANES + lane + 1;          // 1-based knot of this lane
             const bool act = k <= c.N;
             const bool has_u = k < c.N;
             const bool jump = has_u && (k == c.k_trans - 1);   // constraints.jl:29 / :190
+            double* const zk = zbuf + (k - 1) * QL_ZSTRIDE;
 
             // ---- 1. my knot's slice of Z: x_k, u_k, x_{k+1}
             double xk[QL_NX], uk[QL_NU], xnx[QL_NX];
-            {
-                const double* zk = zbuf + (k - 1) * QL_ZSTRIDE;
 #pragma unroll
-                for (int i = 0; i < QL_NX; ++i) xk[i] = act ? zk[i] : 0.0;
+            for (int i = 0; i < QL_NX; ++i) xk[i] = act ? zk[i] : 0.0;
 #pragma unroll
-                for (int i = 0; i < QL_NU; ++i) uk[i] = has_u ? zk[QL_NX + i] : 0.0;
+            for (int i = 0; i < QL_NU; ++i) uk[i] = has_u ? zk[QL_NX + i] : 0.0;
 #pragma unroll
-                for (int i = 0; i < QL_NX; ++i) xnx[i] = has_u ? zk[QL_ZSTRIDE + i] : 0.0;
-            }
-            if (p == c.npass - 1) {
-                // every lane holds its inputs: prefetch the next decision vector over this one
-                __syncwarp();
-                const long long nb = b + gridDim.x;
-                if (nb < P.B) stage_z(P.Z + nb * P.ldz, zaddr, c.n_nlp, lane);
-            }
+            for (int i = 0; i < QL_NX; ++i) xnx[i] = has_u ? zk[QL_ZSTRIDE + i] : 0.0;
+            __syncwarp();       // every lane holds its inputs: this pass's slice of zbuf may be overwritten
 
-            // ---- 2. cost and gradient (costs.jl:6-34, quadratic_cost.jl:44-52)
+            // ---- 2. cost and gradient (costs.jl:6-34, quadratic_cost.jl:44-52); gradient in place over Z
             if (act && (P.f || gradrow)) {
                 const double* ct = P.cost + (k - 1);
                 const int np = P.npad;
-                double hq, dq;
-                {
-                    const double Q0 = __ldg(ct), q0 = __ldg(ct + 15 * np);
-                    hq = __dmul_rn(__dmul_rn(0.5, __dmul_rn(xk[0], Q0)), xk[0]);     // 0.5*x'Q*x, folded left
-                    dq = __dmul_rn(q0, xk[0]);                                        // q'x
-                    const double gq = __dadd_rn(__dmul_rn(Q0, xk[0]), q0);            // Q*x + q
-                    gr[lane * QL_ZSTRIDE] = has_u ? __dmul_rn(uk[4], gq) : gq;
-                }
+                double cq[QL_NCOST];                // all loads first: their latency overlaps
+#pragma unroll
+                for (int i = 0; i < QL_NCOST; ++i) cq[i] = __ldg(ct + i * np);
+                const double hk = uk[4];
+                double hq = __dmul_rn(__dmul_rn(0.5, __dmul_rn(xk[0], cq[0])), xk[0]);     // 0.5*x'Q*x, folded left
+                double dq = __dmul_rn(cq[15], xk[0]);                                       // q'x
 #pragma unroll
                 for (int i = 1; i < QL_NX; ++i) {
-                    const double Qi = __ldg(ct + i * np), qi = __ldg(ct + (15 + i) * np);
-                    hq = __dadd_rn(hq, __dmul_rn(__dmul_rn(0.5, __dmul_rn(xk[i], Qi)), xk[i]));
-                    dq = __dadd_rn(dq, __dmul_rn(qi, xk[i]));
-                    const double gq = __dadd_rn(__dmul_rn(Qi, xk[i]), qi);
-                    gr[lane * QL_ZSTRIDE + i] = has_u ? __dmul_rn(uk[4], gq) : gq;
+                    hq = __dadd_rn(hq, __dmul_rn(__dmul_rn(0.5, __dmul_rn(xk[i], cq[i])), xk[i]));
+                    dq = __dadd_rn(dq, __dmul_rn(cq[15 + i], xk[i]));
                 }
-                const double cc = __ldg(ct + 40 * np);
+#pragma unroll
+                for (int i = 0; i < QL_NX; ++i) {
+                    const double gq = __dadd_rn(__dmul_rn(cq[i], xk[i]), cq[15 + i]);       // Q*x + q
+                    zk[i] = has_u ? __dmul_rn(hk, gq) : gq;
+                }
                 double term;
                 if (has_u) {
-                    const double R0 = __ldg(ct + 30 * np), r0 = __ldg(ct + 35 * np);
-                    double hr = __dmul_rn(__dmul_rn(0.5, __dmul_rn(uk[0], R0)), uk[0]);
-                    double dr = __dmul_rn(r0, uk[0]);
-                    gr[lane * QL_ZSTRIDE + QL_NX] = __dmul_rn(uk[4], __dadd_rn(__dmul_rn(R0, uk[0]), r0));
+                    double hr = __dmul_rn(__dmul_rn(0.5, __dmul_rn(uk[0], cq[30])), uk[0]);
+                    double dr = __dmul_rn(cq[35], uk[0]);
 #pragma unroll
                     for (int i = 1; i < QL_NU; ++i) {
-                        const double Ri = __ldg(ct + (30 + i) * np), ri = __ldg(ct + (35 + i) * np);
-                        hr = __dadd_rn(hr, __dmul_rn(__dmul_rn(0.5, __dmul_rn(uk[i], Ri)), uk[i]));
-                        dr = __dadd_rn(dr, __dmul_rn(ri, uk[i]));
-                        // quirk Q1 (costs.jl:30): the h entry gets h*(R55*h + r5), not d(h*stagecost)/dh
-                        gr[lane * QL_ZSTRIDE + QL_NX + i] = __dmul_rn(uk[4], __dadd_rn(__dmul_rn(Ri, uk[i]), ri));
+                        hr = __dadd_rn(hr, __dmul_rn(__dmul_rn(0.5, __dmul_rn(uk[i], cq[30 + i])), uk[i]));
+                        dr = __dadd_rn(dr, __dmul_rn(cq[35 + i], uk[i]));
                     }
+                    // quirk Q1 (costs.jl:30): the h entry gets h*(R55*h + r5), not d(h*stagecost)/dh
+#pragma unroll
+                    for (int i = 0; i < QL_NU; ++i)
+                        zk[QL_NX + i] = __dmul_rn(hk, __dadd_rn(__dmul_rn(cq[30 + i], uk[i]), cq[35 + i]));
                     // ((((0.5x'Qx + q'x) + 0.5u'Ru) + r'u) + c) * h
-                    const double sc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(hq, dq), hr), dr), cc);
-                    term = __dmul_rn(uk[4], sc);
+                    const double sc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(hq, dq), hr), dr), cq[40]);
+                    term = __dmul_rn(hk, sc);
                 } else {
-                    term = __dadd_rn(__dadd_rn(hq, dq), cc);       // termcost
+                    term = __dadd_rn(__dadd_rn(hq, dq), cq[40]);       // termcost
                 }
                 fsum += term;
             }
@@ -215,19 +237,22 @@ __global__ void __launch_bounds__(QL_LANES) eval_kernel(const __grid_constant__ 
             if (has_u && (WITH_JAC || grow)) {
                 double xn[QL_NX];
                 if (WITH_JAC) {
-                    if (k >= c.k_trans) ql_rk4_jac_mode3(xk, uk, mg, mb, mf, Ib, xn, jv);
-                    else if (c.init_mode == 1) ql_rk4_jac_mode1(xk, uk, mg, mb, mf, Ib, xn, jv);
-                    else ql_rk4_jac_mode2(xk, uk, mg, mb, mf, Ib, xn, jv);
+                    if (k >= c.k_trans) ql_rk4_jac_mode3(xk, uk, K, xn, jv);
+                    else if (c.init_mode == 1) ql_rk4_jac_mode1(xk, uk, K, xn, jv);
+                    else ql_rk4_jac_mode2(xk, uk, K, xn, jv);
                 } else {
-                    if (k >= c.k_trans) ql_rk4_mode3(xk, uk, mg, mb, mf, Ib, xn);
-                    else if (c.init_mode == 1) ql_rk4_mode1(xk, uk, mg, mb, mf, Ib, xn);
-                    else ql_rk4_mode2(xk, uk, mg, mb, mf, Ib, xn);
+                    if (k >= c.k_trans) ql_rk4_mode3(xk, uk, K, xn);
+                    else if (c.init_mode == 1) ql_rk4_mode1(xk, uk, K, xn);
+                    else ql_rk4_mode2(xk, uk, K, xn);
                 }
                 if (jump) {   // jump1_map / jump2_map, planar_quadruped.jl:250-260
                     xn[4] = 0.0; xn[6] = 0.0; xn[10] = 0.0; xn[11] = 0.0; xn[12] = 0.0; xn[13] = 0.0;
                 }
+                if (grow) {   // dynamics defect, constraints.jl:25-36: 15 consecutive rows per knot
+                    double* d = grow + c.c_dyn + (k - 1) * QL_NX;
 #pragma unroll
-                for (int i = 0; i < QL_NX; ++i) gd[lane * QL_NX + i] = __dsub_rn(xn[i], xnx[i]);
+                    for (int i = 0; i < QL_NX; ++i) d[i] = __dsub_rn(xn[i], xnx[i]);
+                }
             }
             if (act && (WITH_JAC || grow)) {
                 double s, co;
@@ -237,7 +262,7 @@ __global__ void __launch_bounds__(QL_LANES) eval_kernel(const __grid_constant__ 
                 if (grow) {
                     grow[c.c_cfirst + (k - 1)] = first_is_y1 ? xk[4] : xk[6];                                   // :58/:60
                     if (k >= c.k_trans) grow[c.c_cother + (k - c.k_trans)] = first_is_y1 ? xk[6] : xk[4];      // :84/:86
-                    grow[c.c_body + (k - 1)] = __dsub_rn(xk[1], __dmul_rn(c.half_lb, fabs(s)));   // :109
+                    grow[c.c_body + (k - 1)] = __dsub_rn(xk[1], __dmul_rn(c.half_lb, fabs(s)));                 // :109
                     if (k == 1) {
                         const double* x0 = P.x0 ? P.x0 + b * QL_NX : P.x0_def;
 #pragma unroll
@@ -252,33 +277,45 @@ __global__ void __launch_bounds__(QL_LANES) eval_kernel(const __grid_constant__ 
                 }
             }
 
-            // ---- 4. flush the pass tiles with coalesced stores
+            // ---- 4. flush this pass's gradient slice (staged in place over Z) with coalesced stores
             __syncwarp();
-            if (grow) {
-                const int k_first = p * QL_LANES + 1;
-                const int ndyn = min(QL_LANES, c.N - k_first) * QL_NX;      // knots k_first.. with k < N
-                double* dst = grow + c.c_dyn + (k_first - 1) * QL_NX;
-                for (int i = lane; i < ndyn; i += QL_LANES) dst[i] = gd[i];
-            }
             if (gradrow) {
                 const int e0 = p * QL_LANES * QL_NZK;
                 const int cnt = min(QL_LANES * QL_NZK, c.n_nlp - e0);
-                for (int i = lane; i < cnt; i += QL_LANES) gradrow[e0 + i] = gr[i + i / QL_NZK];
+                const double* src = zbuf + p * QL_LANES * QL_ZSTRIDE;
+                for (int i = lane; i < cnt; i += QL_LANES) gradrow[e0 + i] = src[i + i / QL_NZK];
+                __syncwarp();
             }
-            __syncwarp();
+            if (p == c.npass - 1) {
+                // zbuf is dead: prefetch the next decision vector while the Jacobian values stream out
+                const long long nb = b + gridDim.x;
+                if (nb < P.B) stage_z(P.Z + nb * P.ldz, zaddr, c.n_nlp, lane);
+            }
 
             // ---- 5. stream this pass's share of the Jacobian values
             if (WITH_JAC) {
+                double* const jrow = P.jac + b * P.ldjac;
                 const int roff = act ? ql_run_off(c, k) : 0;
+                const int e4 = ql_e4(c, k), e6 = ql_e6(c, k), fc = ql_fc(c, k);
                 const int sb = __ldg(P.seg_begin + p), se = __ldg(P.seg_begin + p + 1);
                 for (int s = sb; s < se; ++s) {
-                    const int4 s0 = __ldg(reinterpret_cast<const int4*>(P.segs + s));          // k0 nk start end
-                    const int4 s1 = __ldg(reinterpret_cast<const int4*>(P.segs + s) + 1);      // tmpl buf - -
-                    const int k0 = s0.x, nk = s0.y, start = s0.z, end = s0.w, tm = s1.x, bi = s1.y;
+                    const int4 rec = *reinterpret_cast<const int4*>(plan + s);
+                    const int start = rec.x, end = rec.y;
+                    const int k0 = (int)(short)(rec.z & 0xffff), nk = (int)(signed char)((rec.z >> 16) & 0xff);
+                    const int bi = (rec.z >> 24) & 0xff, tm = (int)(short)(rec.w & 0xffff);
                     double* const buf = jb + bi * QL_JBUF;
                     const unsigned baddr = jaddr + (unsigned)bi * (QL_JBUF * 8u);
                     const int base = start & ~1;                 // image[0] <-> stream offset `base`
                     const bool mine = act && k >= k0 && k < k0 + nk;
+                    const unsigned raddr = baddr + 8u * (unsigned)(roff - base);
+                    unsigned pg[7];                              // run start + extras preceding each column group
+                    pg[0] = raddr;
+                    pg[1] = raddr + 8u;
+                    pg[2] = raddr + 16u;
+                    pg[3] = raddr + 8u * (2 + e4);
+                    pg[4] = raddr + 8u * (2 + e4 + e6);
+                    pg[5] = raddr + 8u * (2 + e4 + e6 + fc);
+                    pg[6] = raddr + 8u * (2 + e4 + e6 + 2 * fc);
 
                     // the bulk store issued two segments ago read this buffer: wait until it is done
                     if (P.bulk && lane == 0) bulk_wait_read<1>();
@@ -287,21 +324,18 @@ __global__ void __launch_bounds__(QL_LANES) eval_kernel(const __grid_constant__ 
                     if ((bi ? tmpl1 : tmpl0) != tm) {            // different constant image: rebuild
                         for (int i = lane; i < QL_JBUF / 2; i += QL_LANES) st_shared_zero16(baddr + 16u * i);
                         __syncwarp();
-                        if (mine) ql_write_run_constants(c, k, buf + (roff - base));
+                        if (mine) {
+                            ql_write_run_constants(c, k, buf + (roff - base));
+                            if (has_u) {
+                                if (k >= c.k_trans) ql_const_mode3(pg, jump);
+                                else if (c.init_mode == 1) ql_const_mode1(pg, jump);
+                                else ql_const_mode2(pg, jump);
+                            }
+                        }
                         if (bi) tmpl1 = tm; else tmpl0 = tm;
                     }
                     if (mine) {
-                        const unsigned raddr = baddr + 8u * (unsigned)(roff - base);
                         if (has_u) {
-                            const int e4 = ql_e4(c, k), e6 = ql_e6(c, k), fc = ql_fc(c, k);
-                            unsigned pg[7];
-                            pg[0] = raddr;
-                            pg[1] = raddr + 8u;
-                            pg[2] = raddr + 16u;
-                            pg[3] = raddr + 8u * (2 + e4);
-                            pg[4] = raddr + 8u * (2 + e4 + e6);
-                            pg[5] = raddr + 8u * (2 + e4 + e6 + fc);
-                            pg[6] = raddr + 8u * (2 + e4 + e6 + 2 * fc);
                             if (k >= c.k_trans) ql_patch_mode3(jv, pg, jump);
                             else if (c.init_mode == 1) ql_patch_mode1(jv, pg, jump);
                             else ql_patch_mode2(jv, pg, jump);

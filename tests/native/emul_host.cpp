@@ -7,12 +7,7 @@
 #include <cstring>
 #include <vector>
 
-#define QL_ADD(a, b) ((a) + (b))
-#define QL_SUB(a, b) ((a) - (b))
-#define QL_MUL(a, b) ((a) * (b))
-#define QL_DIV(a, b) ((a) / (b))
-#define QL_FN static inline
-#define QL_ST(ptr, off, val) ((ptr)[(off)] = (val))
+#include "host_consts.h"
 #include "../../quadruped_landing_b200/csrc/layout.h"
 #include "../../quadruped_landing_b200/csrc/rk4_dual_gen.h"
 
@@ -36,9 +31,21 @@ int emul_jac_stream(int N, int k_trans, int init_mode, double g, double mb, doub
             const int base = start & ~1;
             if (end - base > QL_JBUF) return -2;
             double* buf = bufs[bi].data();
+            const HostConsts K{c.g, c.mb, c.mf, c.Ib};
             if (tmpl[bi] != tm) {
                 std::memset(buf, 0, sizeof(double) * QL_JBUF);
-                for (int k = k0; k < k0 + nk; ++k) ql_write_run_constants(c, k, buf + (ql_run_off(c, k) - base));
+                for (int k = k0; k < k0 + nk; ++k) {
+                    double* run = buf + (ql_run_off(c, k) - base);
+                    ql_write_run_constants(c, k, run);
+                    if (k < N) {
+                        double* p[7];
+                        for (int grp = 0; grp < 7; ++grp) p[grp] = run + ql_group_shift(c, k, grp);
+                        const bool jump = (k == k_trans - 1);
+                        if (k >= k_trans) ql_const_mode3(p, jump);
+                        else if (init_mode == 1) ql_const_mode1(p, jump);
+                        else ql_const_mode2(p, jump);
+                    }
+                }
                 tmpl[bi] = tm;
             }
             for (int k = k0; k < k0 + nk; ++k) {
@@ -50,9 +57,9 @@ int emul_jac_stream(int N, int k_trans, int init_mode, double g, double mb, doub
                     double* p[7];
                     for (int grp = 0; grp < 7; ++grp) p[grp] = run + ql_group_shift(c, k, grp);
                     const bool jump = (k == k_trans - 1);
-                    if (k >= k_trans) { ql_rk4_jac_mode3(x, u, c.g, c.mb, c.mf, c.Ib, xn, jv); ql_patch_mode3(jv, p, jump); }
-                    else if (init_mode == 1) { ql_rk4_jac_mode1(x, u, c.g, c.mb, c.mf, c.Ib, xn, jv); ql_patch_mode1(jv, p, jump); }
-                    else { ql_rk4_jac_mode2(x, u, c.g, c.mb, c.mf, c.Ib, xn, jv); ql_patch_mode2(jv, p, jump); }
+                    if (k >= k_trans) { ql_rk4_jac_mode3(x, u, K, xn, jv); ql_patch_mode3(jv, p, jump); }
+                    else if (init_mode == 1) { ql_rk4_jac_mode1(x, u, K, xn, jv); ql_patch_mode1(jv, p, jump); }
+                    else { ql_rk4_jac_mode2(x, u, K, xn, jv); ql_patch_mode2(jv, p, jump); }
                 }
                 const double th = x[2];
                 run[ql_theta_pos(c, k)] = (th > 0) ? (-c.half_lb) * std::cos(th) : c.half_lb * std::cos(th);

@@ -40,8 +40,8 @@ def assert_same_bits(nlp, got, ref, what=""):
         else:
             trig = np.zeros(nlp.n_nlp, dtype=bool)
         assert np.array_equal(a[..., ~trig], b[..., ~trig]), f"{what}{k}: bits differ outside the sin/cos entries"
-        ulp = np.abs(a[..., trig] - b[..., trig]) / np.spacing(np.abs(b[..., trig]) + 1e-300)
-        assert ulp.size == 0 or ulp.max() <= 2, f"{what}{k}: sin/cos entries differ by {ulp.max()} ulp"
+        d = np.abs(a[..., trig] - b[..., trig])      # operands are O(1): a few ulp(1) at most
+        assert d.size == 0 or d.max() <= 4 * np.finfo(np.float64).eps, f"{what}{k}: sin/cos entries differ by {d.max()}"
     if "f" in got:
         assert_parity(got["f"], ref["f"], f"{what}f")
 

@@ -61,6 +61,17 @@ def test_other_model_constants(rk4_host_lib):
             assert np.array_equal(xn, xn0) and np.array_equal(J.reshape(20, 15).T, J0)
 
 
+@pytest.mark.parametrize("b", [10.0, 0.1, 10.0 * (0.5 * 0.5) / 12, 6.0, 7.3, 0.23, 3.0, 1.9999999999999998])
+def test_reciprocal_fma_division_is_correctly_rounded(rk4_host_lib, b):
+    """The kernel divides by model constants as q = a*r, q' = fma(fma(-q, b, a), r, q) with r = RN(1/b);
+    it must equal the IEEE quotient the reference computes (also re-checked at qlnlp_create)."""
+    import ctypes as C
+    fn = rk4_host_lib.host_count_fastdiv_mismatches
+    fn.restype = C.c_longlong
+    fn.argtypes = [C.c_double, C.c_longlong, C.c_ulonglong]
+    assert fn(b, 3_000_000, 2024) == 0
+
+
 def test_committed_header_is_up_to_date(tmp_path):
     gen = os.path.join(ROOT, "tools", "gen_rk4_dual.py")
     hdr = os.path.join(ROOT, "quadruped_landing_b200", "csrc", "rk4_dual_gen.h")

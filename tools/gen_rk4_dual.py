@@ -254,7 +254,7 @@ def emit_body(g, outputs, indent="    "):
         if key[0] == "c":
             return repr(key[1])
         if key[0] == "in":
-            return key[1]
+            return key[1] if "[" in key[1] else "K." + key[1]
         return f"t{n}"
 
     lines = []
@@ -266,8 +266,14 @@ def emit_body(g, outputs, indent="    "):
         counts[op] += 1
         if op == "neg":
             lines.append(f"{indent}const double t{n} = -{ref(key[1])};")
+        elif op == "div":
+            # every divisor is a model constant (mb, mf, Ib) or the literal 6.0: name it, so the includer
+            # can divide exactly with a precomputed reciprocal (QL_DIV_<name>(a) == RN(a / name))
+            d = g.nodes[key[2]]
+            name = {"mb": "MB", "mf": "MF", "Ib": "IB"}[d[1]] if d[0] == "in" else {6.0: "SIX"}[d[1]]
+            lines.append(f"{indent}const double t{n} = QL_DIV_{name}({ref(key[1])});")
         else:
-            mac = {"add": "QL_ADD", "sub": "QL_SUB", "mul": "QL_MUL", "div": "QL_DIV"}[op]
+            mac = {"add": "QL_ADD", "sub": "QL_SUB", "mul": "QL_MUL"}[op]
             lines.append(f"{indent}const double t{n} = {mac}({ref(key[1])}, {ref(key[2])});")
     for lhs, n in outputs:
         lines.append(f"{indent}{lhs} = {ref(n)};")
@@ -320,7 +326,9 @@ def main():
     w("// rules exactly; operations whose result is exact (x*0, x*1, x+0, ...) are removed, so")
     w("// the results are bit-identical to the dense 20-wide dual evaluation for finite inputs.")
     w("//")
-    w("// The includer defines QL_ADD/QL_SUB/QL_MUL/QL_DIV (round-to-nearest, NO fma contraction),")
+    w("// The includer defines QL_ADD/QL_SUB/QL_MUL (round-to-nearest, NO fma contraction),")
+    w("// QL_DIV_MB/QL_DIV_MF/QL_DIV_IB/QL_DIV_SIX(a) (correctly rounded a/mb, a/mf, a/Ib, a/6.0; they may use")
+    w("// the constants object K, whose type KT also provides the fields K.g, K.mb, K.mf, K.Ib),")
     w("// QL_FN (function qualifiers) and QL_ST(ptr, off, val) (store of one double).")
     w("#pragma once")
     w("")
@@ -330,8 +338,8 @@ def main():
         g, xn = build(mode, False)
         lines, cnt = emit_body(g, [(f"xn[{i}]", xn[i].v) for i in range(NX)])
         w(f"// mode {mode}, values only: {cnt}")
-        w(f"QL_FN void ql_rk4_mode{mode}(const double* x, const double* u, double g, double mb, double mf, double Ib,")
-        w(f"                           double* xn)")
+        w(f"template <typename KT>")
+        w(f"QL_FN void ql_rk4_mode{mode}(const double* x, const double* u, const KT& K, double* xn)")
         w("{")
         out.extend(lines)
         w("}")
@@ -340,35 +348,51 @@ def main():
         # with partials
         g, xn = build(mode, True)
         pat = pattern_of(g, xn)
+        var = [(i, j) for (i, j) in pat if not g.is_const(xn[i].part(j))]
+        con = [(i, j) for (i, j) in pat if g.is_const(xn[i].part(j))]
         outs = [(f"xn[{i}]", xn[i].v) for i in range(NX)]
-        outs += [(f"jv[{n}]", xn[i].part(j)) for n, (i, j) in enumerate(pat)]
+        outs += [(f"jv[{n}]", xn[i].part(j)) for n, (i, j) in enumerate(var)]
         lines, cnt = emit_body(g, outs)
-        nconst = sum(1 for (i, j) in pat if g.is_const(xn[i].part(j)))
-        w(f"// mode {mode}, values + Jacobian pattern ({len(pat)} entries, {nconst} of them constants): {cnt}")
-        w(f"#define QL_NJ_MODE{mode} {len(pat)}")
-        w(f"QL_FN void ql_rk4_jac_mode{mode}(const double* x, const double* u, double g, double mb, double mf, double Ib,")
-        w(f"                               double* xn, double* jv)")
+        w(f"// mode {mode}, values + Jacobian: pattern of {len(pat)} entries = {len(var)} value-dependent (jv) + {len(con)} constants: {cnt}")
+        w(f"#define QL_NJ_MODE{mode} {len(var)}")
+        w(f"#define QL_NJC_MODE{mode} {len(con)}")
+        w(f"template <typename KT>")
+        w(f"QL_FN void ql_rk4_jac_mode{mode}(const double* x, const double* u, const KT& K, double* xn, double* jv)")
         w("{")
         out.extend(lines)
         w("}")
         w("")
-        w(f"// pattern of mode {mode}: jv[n] = d xn[PAT_I[n]] / d z[PAT_J[n]], column-major order")
-        w(f"static const unsigned char QL_PAT_I_MODE{mode}[{len(pat)}] = {{{', '.join(str(i) for i, _ in pat)}}};")
-        w(f"static const unsigned char QL_PAT_J_MODE{mode}[{len(pat)}] = {{{', '.join(str(j) for _, j in pat)}}};")
+        w(f"// value-dependent entries of mode {mode}: jv[n] = d xn[PAT_I[n]] / d z[PAT_J[n]], column-major order")
+        w(f"static const unsigned char QL_PAT_I_MODE{mode}[{len(var)}] = {{{', '.join(str(i) for i, _ in var)}}};")
+        w(f"static const unsigned char QL_PAT_J_MODE{mode}[{len(var)}] = {{{', '.join(str(j) for _, j in var)}}};")
+        w(f"// constant entries of mode {mode} (value QL_CPAT_V)")
+        w(f"static const unsigned char QL_CPAT_I_MODE{mode}[{len(con)}] = {{{', '.join(str(i) for i, _ in con)}}};")
+        w(f"static const unsigned char QL_CPAT_J_MODE{mode}[{len(con)}] = {{{', '.join(str(j) for _, j in con)}}};")
+        w(f"static const double QL_CPAT_V_MODE{mode}[{len(con)}] = {{{', '.join(repr(g.cval(xn[i].part(j))) for i, j in con)}}};")
         w("")
-        w(f"// Patch jv[] into a knot's run.  p[grp] points at the run start shifted by the extras that")
-        w(f"// precede column group grp (layout.h: ql_col_group / ql_group_shift).  `jump` applies the")
+        keep = (1, 1, 1, 1, 0, 1, 0, 1, 1, 1, 0, 0, 0, 0, 0)
+        w(f"// Patch the value-dependent entries into a knot's run.  p[grp] addresses the run start shifted by the")
+        w(f"// extras that precede column group grp (layout.h: ql_col_group / ql_group_shift).  `jump` applies the")
         w(f"// reference's jump Jacobian Diagonal([1,1,1,1,0,1,0,1,1,1,0,0,0,0,0]) (planar_quadruped.jl:262-263).")
         w(f"template <typename PTR>")
         w(f"QL_FN void ql_patch_mode{mode}(const double* jv, const PTR* p, bool jump)")
         w("{")
-        keep = (1, 1, 1, 1, 0, 1, 0, 1, 1, 1, 0, 0, 0, 0, 0)
-        for n, (i, j) in enumerate(pat):
+        for n, (i, j) in enumerate(var):
             val = f"jv[{n}]" if keep[i] else f"(jump ? 0.0 : jv[{n}])"
             w(f"    QL_ST(p[{col_group(j)}], {rk4_offset(i, j)}, {val});")
         w("}")
         w("")
-        summary.append((mode, "jac", cnt, len(pat)))
+        w(f"// The constant entries (part of a staging buffer's persistent image; rewritten only on a rebuild).")
+        w(f"template <typename PTR>")
+        w(f"QL_FN void ql_const_mode{mode}(const PTR* p, bool jump)")
+        w("{")
+        for (i, j) in con:
+            v = repr(g.cval(xn[i].part(j)))
+            val = v if keep[i] else f"(jump ? 0.0 : {v})"
+            w(f"    QL_ST(p[{col_group(j)}], {rk4_offset(i, j)}, {val});")
+        w("}")
+        w("")
+        summary.append((mode, "jac", cnt, len(var), len(con)))
     text = "\n".join(out) + "\n"
     with open(OUT, "w") as f:
         f.write(text)
