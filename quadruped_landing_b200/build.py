@@ -53,5 +53,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines) -> str:
+    """Compile an experimental variant (extra -D flags) to libqlnlp_<name>.so for A/B timing (tools/ab_bench.py)."""
+    out = os.path.join(_HERE, f"libqlnlp_{name}.so")
+    cmd = [nvcc_path(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

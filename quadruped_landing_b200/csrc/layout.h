@@ -26,7 +26,6 @@
 #define QL_NU 5
 #define QL_NZK 20
 #define QL_LANES 32           // knots per pass: one lane per knot
-#define QL_ZSTRIDE 21         // padded knot stride of the staged decision vector (odd => conflict-free)
 #define QL_JBUF 1064          // doubles per J staging buffer: two runs (<= 529 + 531) + parity, rounded to 16 B
 #define QL_MAX_N 1024
 #define QL_NCOST 41           // cost fields per knot: Q[15] q[15] R[5] r[5] c

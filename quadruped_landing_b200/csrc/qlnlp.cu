@@ -250,6 +250,7 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     P.jac = io->jac; P.ldjac = io->ldjac;
     P.B = B;
     P.bulk = (io->jac && (reinterpret_cast<uintptr_t>(io->jac) & 15) == 0 && (io->ldjac & 1) == 0) ? 1 : 0;
+    P.zbulk = ((reinterpret_cast<uintptr_t>(io->Z) & 15) == 0 && (io->ldz & 1) == 0) ? 1 : 0;   // ldz even > n_nlp (odd)
 
     const int wj = io->jac ? 1 : 0;
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm[wj];

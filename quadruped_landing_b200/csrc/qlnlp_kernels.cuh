@@ -2,15 +2,16 @@
 //
 // One warp per trajectory (decision vector), one lane per knot, ceil(N/32) passes; one warp per
 // CTA so warps never synchronise with each other.  Per evaluation the warp
-//   1. stages Z through shared memory (cp.async, coalesced 8-byte elements, knot stride padded
-//      to 21 doubles so the lane-per-knot reads are bank-conflict free); the next decision vector is
-//      prefetched while the last pass streams its Jacobian values,
+//   1. stages Z through shared memory with ONE TMA bulk load per decision vector
+//      (cp.async.bulk.shared.global + mbarrier; plain cp.async when Z is not 16-byte aligned); the next
+//      vector is prefetched while the last pass streams its Jacobian values,
 //   2. evaluates, per lane, the quadratic stage cost + gradient (costs.jl:6-34), one RK4 step of
 //      the hybrid dynamics and its defect (constraints.jl:6-41), the contact / final-force /
 //      body-clearance rows (constraints.jl:48-113,154) and the value-dependent entries of the
 //      15x20 RK4 Jacobian by forward-mode duals held in registers (rk4_dual_gen.h),
-//   3. writes the gradient in place over its slice of the staged Z and flushes it with coalesced
-//      stores; reduces the cost over the warp with shuffles,
+//   3. writes the gradient, then the dynamics defects, in place over its (dead) slice of the staged Z and
+//      flushes each with coalesced full-sector stores (scattered 8-byte stores of the defects cost 11 %
+//      of throughput in the A/B runs of profiles/r01_ablation.md); reduces the cost with warp shuffles,
 //   4. streams the SPARSE_BLOCK Jacobian values: the value stream is a concatenation of per-knot
 //      runs (layout.h) that are ~90 % structural constants, so each 1-2-knot segment lives in a
 //      shared-memory image whose constants persist from one evaluation to the next; the owner
@@ -63,6 +64,32 @@ __device__ __forceinline__ void bulk_wait_read()
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// TMA bulk copy global -> shared::cta, completion signalled on an mbarrier
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned sdst, const void* gsrc, unsigned bytes, unsigned mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst),
+                 "l"(gsrc), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QL_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra QL_DONE_%=;\n"
+        "bra QL_WAIT_%=;\n"
+        "QL_DONE_%=:\n"
+        "}\n" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
 // make generic-proxy shared-memory writes visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -121,21 +148,30 @@ struct Launch {
     double* jac; long long ldjac;
     long long B;
     int bulk;                  // 1: jac rows are 16 B aligned -> TMA bulk stores
+    int zbulk;                 // 1: Z rows are 16 B aligned and ldz > n_nlp -> one TMA bulk load per vector
 };
 
-// shared memory carve-up (doubles): staged Z | two J staging buffers | segment plan
-__host__ __device__ inline int zbuf_len(int N) { return (QL_ZSTRIDE * N + 1) & ~1; }
+// shared memory carve-up: staged Z (same layout as in HBM) | mbarrier | two J staging buffers | segment plan
+__host__ __device__ inline int zbuf_len(int N) { return QL_NZK * N + 2; }     // n_nlp + 1 rounded up to even, + mbarrier
 __host__ __device__ inline size_t smem_bytes(int N, bool with_jac)
 {
     const int nseg_max = (N + 1) / 2 + (N + QL_LANES - 1) / QL_LANES;
     return sizeof(double) * (size_t)zbuf_len(N) + (with_jac ? sizeof(double) * 2 * QL_JBUF + sizeof(QlSeg) * nseg_max : 0);
 }
 
-// cp.async the decision vector into the padded shared layout (element e -> e + e/20)
-__device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigned zaddr, int n, int lane)
+// Start fetching a decision vector into shared memory.  zbulk: one TMA bulk load of n+1 doubles (n is odd, the
+// row is 16-byte aligned with ldz > n, so the extra element is in bounds); else coalesced 8-byte cp.async.
+__device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigned zaddr, unsigned mbar, int n, int lane,
+                                        bool zbulk)
 {
-    for (int e = lane; e < n; e += QL_LANES) cp_async_8(zaddr + 8u * (unsigned)(e + e / QL_NZK), Zrow + e);
-    cp_async_commit();
+    if (zbulk) {
+        fence_proxy_async();        // order this warp's earlier generic accesses to zbuf before the async write
+        __syncwarp();
+        if (lane == 0) bulk_load(zaddr, Zrow, 8u * (unsigned)(n + 1), mbar);
+    } else {
+        for (int e = lane; e < n; e += QL_LANES) cp_async_8(zaddr + 8u * (unsigned)e, Zrow + e);
+        cp_async_commit();
+    }
 }
 
 template <bool WITH_JAC, bool FASTDIV>
@@ -146,6 +182,7 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
     const int lane = threadIdx.x;
 
     double* const zbuf = smem;
+    const unsigned mbar = smem_addr(zbuf + zbuf_len(c.N) - 1);      // 8-byte mbarrier behind the staged vector
     double* const jb = zbuf + zbuf_len(c.N);
     QlSeg* const plan = reinterpret_cast<QlSeg*>(jb + 2 * QL_JBUF);
     const unsigned zaddr = smem_addr(zbuf);
@@ -156,8 +193,15 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
     K.g = c.g; K.mb = c.mb; K.mf = c.mf; K.Ib = c.Ib; K.rmb = P.rmb; K.rmf = P.rmf; K.rIb = P.rIb;
     const bool first_is_y1 = (c.init_mode == 1);    // contact-first reads y1 (mode 1) or y2 (mode 2)
 
+    const bool zbulk = P.zbulk != 0;
+    unsigned zphase = 0;                 // parity of the mbarrier phase the next wait completes
+    if (zbulk) {
+        if (lane == 0) mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
     long long b = blockIdx.x;
-    if (b < P.B) stage_z(P.Z + b * P.ldz, zaddr, c.n_nlp, lane);
+    if (b < P.B) stage_z(P.Z + b * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
     if (WITH_JAC) {
         // the segment plan lives in shared memory: one 16-byte record per segment
         const int4* src = reinterpret_cast<const int4*>(P.segs);
@@ -166,7 +210,8 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
     }
 
     for (; b < P.B; b += gridDim.x) {
-        cp_async_wait_all();
+        if (zbulk) { mbar_wait(mbar, zphase); zphase ^= 1u; }
+        else cp_async_wait_all();
         __syncwarp();
         double fsum = 0.0;
         double* const grow = P.g ? P.g + b * P.ldg : nullptr;
@@ -177,7 +222,7 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
             const bool act = k <= c.N;
             const bool has_u = k < c.N;
             const bool jump = has_u && (k == c.k_trans - 1);   // constraints.jl:29 / :190
-            double* const zk = zbuf + (k - 1) * QL_ZSTRIDE;
+            double* const zk = zbuf + (k - 1) * QL_NZK;
 
             // ---- 1. my knot's slice of Z: x_k, u_k, x_{k+1}
             double xk[QL_NX], uk[QL_NU], xnx[QL_NX];
@@ -186,7 +231,7 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
 #pragma unroll
             for (int i = 0; i < QL_NU; ++i) uk[i] = has_u ? zk[QL_NX + i] : 0.0;
 #pragma unroll
-            for (int i = 0; i < QL_NX; ++i) xnx[i] = has_u ? zk[QL_ZSTRIDE + i] : 0.0;
+            for (int i = 0; i < QL_NX; ++i) xnx[i] = has_u ? zk[QL_NZK + i] : 0.0;
             __syncwarp();       // every lane holds its inputs: this pass's slice of zbuf may be overwritten
 
             // ---- 2. cost and gradient (costs.jl:6-34, quadratic_cost.jl:44-52); gradient in place over Z
@@ -231,6 +276,16 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
                 fsum += term;
             }
 
+            // flush this pass's gradient slice with coalesced stores; the slice is then free for the defects
+            double* const slice = zbuf + p * QL_LANES * QL_NZK;
+            if (gradrow) {
+                __syncwarp();
+                const int e0 = p * QL_LANES * QL_NZK;
+                const int cnt = min(QL_LANES * QL_NZK, c.n_nlp - e0);
+                for (int i = lane; i < cnt; i += QL_LANES) gradrow[e0 + i] = slice[i];
+                __syncwarp();
+            }
+
             // ---- 3. constraints (constraints.jl:145-158) and the RK4 Jacobian values
             double jv[WITH_JAC ? QL_NJ_MAX : 1];
             double jtheta = 0.0;
@@ -248,10 +303,9 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
                 if (jump) {   // jump1_map / jump2_map, planar_quadruped.jl:250-260
                     xn[4] = 0.0; xn[6] = 0.0; xn[10] = 0.0; xn[11] = 0.0; xn[12] = 0.0; xn[13] = 0.0;
                 }
-                if (grow) {   // dynamics defect, constraints.jl:25-36: 15 consecutive rows per knot
-                    double* d = grow + c.c_dyn + (k - 1) * QL_NX;
+                if (grow) {   // dynamics defect, constraints.jl:25-36: 15 consecutive rows per knot, staged in my slice
 #pragma unroll
-                    for (int i = 0; i < QL_NX; ++i) d[i] = __dsub_rn(xn[i], xnx[i]);
+                    for (int i = 0; i < QL_NX; ++i) slice[lane * QL_NX + i] = __dsub_rn(xn[i], xnx[i]);
                 }
             }
             if (act && (WITH_JAC || grow)) {
@@ -277,19 +331,19 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
                 }
             }
 
-            // ---- 4. flush this pass's gradient slice (staged in place over Z) with coalesced stores
+            // ---- 4. flush this pass's dynamics defects with coalesced stores
             __syncwarp();
-            if (gradrow) {
-                const int e0 = p * QL_LANES * QL_NZK;
-                const int cnt = min(QL_LANES * QL_NZK, c.n_nlp - e0);
-                const double* src = zbuf + p * QL_LANES * QL_ZSTRIDE;
-                for (int i = lane; i < cnt; i += QL_LANES) gradrow[e0 + i] = src[i + i / QL_NZK];
+            if (grow) {
+                const int k_first = p * QL_LANES + 1;
+                const int ndyn = min(QL_LANES, c.N - k_first) * QL_NX;      // knots of this pass with k < N
+                double* dst = grow + c.c_dyn + (k_first - 1) * QL_NX;
+                for (int i = lane; i < ndyn; i += QL_LANES) dst[i] = slice[i];
                 __syncwarp();
             }
             if (p == c.npass - 1) {
                 // zbuf is dead: prefetch the next decision vector while the Jacobian values stream out
                 const long long nb = b + gridDim.x;
-                if (nb < P.B) stage_z(P.Z + nb * P.ldz, zaddr, c.n_nlp, lane);
+                if (nb < P.B) stage_z(P.Z + nb * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
             }
 
             // ---- 5. stream this pass's share of the Jacobian values

@@ -68,9 +68,11 @@ def load_library(rebuild_if_stale: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if rebuild_if_stale and _build.is_stale():
-        path = _build.build()
+    path = os.environ.get("QLNLP_LIB")          # experimental variants (tools/ab_bench.py)
+    if not path:
+        path = _build.LIB
+        if rebuild_if_stale and _build.is_stale():
+            path = _build.build()
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: build it with `python -m quadruped_landing_b200.build` "
                            "(the evaluator has no CPU fallback)")

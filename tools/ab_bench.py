@@ -1,0 +1,72 @@
+"""A/B timing of kernel variants on the GPU: each variant .so is timed in its own subprocess.
+
+    python tools/ab_bench.py build   name=DEF1,DEF2 ...     (CPU box: compiles libqlnlp_<name>.so)
+    python tools/ab_bench.py run     name ...               (GPU box: times each, prints a table)
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CHILD = r'''
+import sys, os, json
+sys.path.insert(0, %r)
+import numpy as np, torch
+import quadruped_landing_b200 as ql
+p = ql.default_problem()
+nlp = ql.HybridNLP.from_problem(p)
+rng = np.random.default_rng(0)
+Z = ql.initial_guess(p)[None, :] + 1e-2 * rng.standard_normal((4096, p.n_nlp))
+Z[:, 19::20] = np.clip(Z[:, 19::20], 1e-3, 2e-2)
+res = {}
+for Bt in (4096, 65536):
+    Zt = torch.from_numpy(Z).cuda().repeat(Bt // 4096, 1).contiguous()
+    out = nlp.eval_batch(Zt)
+    torch.cuda.synchronize()
+    for want in (("f", "grad", "g", "jac"), ("g", "jac")):
+        for _ in range(20):
+            nlp.eval_batch(Zt, out=out, want=want)
+        torch.cuda.synchronize()
+        best = 1e9
+        for rep in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 50 if Bt == 4096 else 8
+            e0.record()
+            for _ in range(n):
+                nlp.eval_batch(Zt, out=out, want=want)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / n)
+        res[f"{Bt}:{'+'.join(want)}"] = Bt / best * 1e3 / 1e6
+print(json.dumps(res))
+''' % ROOT
+
+
+def main():
+    mode, args = sys.argv[1], sys.argv[2:]
+    if mode == "build":
+        from quadruped_landing_b200 import build
+        for a in args:
+            name, _, defs = a.partition("=")
+            print(build.build_variant(name, [d for d in defs.split(",") if d]))
+    else:
+        rows = []
+        for name in args:
+            lib = os.path.join(ROOT, "quadruped_landing_b200", f"libqlnlp_{name}.so" if name != "default" else "libqlnlp.so")
+            env = dict(os.environ, QLNLP_LIB=lib)
+            r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
+            if r.returncode != 0:
+                print(name, "FAILED", r.stderr[-500:])
+                continue
+            rows.append((name, json.loads(r.stdout.strip().splitlines()[-1])))
+        keys = list(rows[0][1]) if rows else []
+        print(f"{'variant':28s}" + "".join(f"{k:>24s}" for k in keys) + "   (M evals/s)")
+        for name, d in rows:
+            print(f"{name:28s}" + "".join(f"{d[k]:24.3f}" for k in keys))
+
+
+if __name__ == "__main__":
+    main()
