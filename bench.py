@@ -26,6 +26,7 @@ if ROOT not in sys.path:
 
 import numpy as np
 
+_emit = print
 METRIC = "batched NLP evals/s (g+sparse Jacobian)"
 UNIT = "evals/s"
 B_PER_GPU = 4096
@@ -135,6 +136,15 @@ def recorded_traffic():
         return None
 
 
+def host_cores():
+    """Threads the CPU baseline uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1,
+    so the OpenMP default is not trusted; the count is passed to the oracle's num_threads clause)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 class CpuRunner:
     """The CPU restatement (oracle port) on the host cores: all four outputs, SPARSE_BLOCK Jacobian.
     Buffers are allocated and first-touched once; step() times one pass over the sample."""
@@ -168,7 +178,7 @@ def run_reference(args):
     from oracle.oracle import Oracle
     prob = ql.default_problem()
     Z = make_inputs(prob, 0, 1)[0]
-    cores = Oracle.max_threads()
+    cores = host_cores()
     sample = 1024 if cores < 32 else B_PER_GPU          # bounded: a few seconds per step on any box
     Zs = Z[:sample]
     runner = CpuRunner(prob, Zs, cores)
@@ -196,7 +206,7 @@ def run_reference(args):
                 "no julia binary exists in the image.  The only recorded Julia figure is ~23 evals/s, 1 thread "
                 "(src/main.ipynb:717-725).",
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def run_gpu(args):
@@ -324,15 +334,14 @@ def run_gpu(args):
         }
         # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same batch
         if n_gpus == 1 and not args.no_cpu:
-            from oracle.oracle import Oracle
-            cores = Oracle.max_threads()
+            cores = host_cores()
             sample = 1024 if cores < 32 else B_PER_GPU
             runner = CpuRunner(prob, host_sets[0][:sample], cores)
             v = sample / statistics.median([runner.step() for _ in range(3)])
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} decision vectors of the same batch, 3 repetitions (median), "
                                               "OpenMP over the batch on all host cores"}
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -347,6 +356,13 @@ def main():
     ap.add_argument("--min-warmup-s", type=float, default=0.5,
                     help="keep warming up until this much load has run (SM clocks ramp from idle); 0 under ncu")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries (e.g. NCCL's version banner) also write to fd 1, so
+    # point fd 1 at stderr while running and emit the line on the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda line: os.write(real_stdout, (line + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:
