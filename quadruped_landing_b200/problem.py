@@ -236,3 +236,48 @@ def initial_guess(prob: ProblemData, dt: float = 0.009) -> np.ndarray:
         X[k][NX - 1] = X[k - 1][NX - 1] + (0.001 if k < kt else 0.02)
     _, Uref = reference_trajectory(prob.model, N, kt, xterm, prob.init_mode, dt)
     return packZ(N, X, Uref)
+
+
+# ---- batches of problems / guesses and the reference's on-disk format -----------------
+def sweep_initial_states(model: PlanarQuadruped, h_drops, theta0_degs) -> np.ndarray:
+    """x0 of every problem of a drop-height x initial-pitch sweep (cf. main.ipynb:92-93,118,122)."""
+    return np.stack([default_states(model, h_drop=float(h), theta0_deg=float(t))[0]
+                     for h in h_drops for t in theta0_degs])
+
+
+def initial_guess_batch(prob: ProblemData, x0_batch, dt: float = 0.009, xp=np):
+    """Cell-7 guess (main.ipynb:181-196) for many initial states at once.  ``xp`` is numpy or torch: with torch
+    tensors on the GPU the guesses are built on the device, so a sweep needs no host-to-device traffic."""
+    N, kt = prob.N, prob.k_trans
+    base = initial_guess(prob, dt)                       # the class guess: everything that does not depend on x0
+    if xp is np:
+        x0_batch = np.asarray(x0_batch, dtype=np.float64)
+        Z = np.tile(base, (x0_batch.shape[0], 1))
+        xterm = prob.xf
+        for k in range(1, kt + 1):                       # Xguess[k] = xinit + (xterm - xinit)/(k_trans-1)*(k-1)
+            Z[:, (k - 1) * NZK:(k - 1) * NZK + 14] = (x0_batch + (xterm - x0_batch) / (kt - 1) * (k - 1))[:, :14]
+        return Z
+    import torch
+    Z = torch.from_numpy(base).to(x0_batch.device).repeat(x0_batch.shape[0], 1)
+    xterm = torch.from_numpy(prob.xf).to(x0_batch.device)
+    for k in range(1, kt + 1):
+        Z[:, (k - 1) * NZK:(k - 1) * NZK + 14] = (x0_batch + (xterm - x0_batch) / (kt - 1) * (k - 1))[:, :14]
+    return Z
+
+
+def save_solution_csv(path: str, Z) -> None:
+    """`writedlm("data_6.csv", Z_sol, ',')` (main.ipynb:881): one value per line, full round-trip precision."""
+    np.savetxt(path, np.asarray(Z, dtype=np.float64).reshape(-1), fmt="%.17g", delimiter=",")
+
+
+def load_solution_csv(path: str) -> np.ndarray:
+    """Reads a solution written by the reference or by ``save_solution_csv`` (plot_data.py:12 does the same)."""
+    return np.loadtxt(path, delimiter=",").reshape(-1)
+
+
+def solution_table(Z, N: int) -> np.ndarray:
+    """The `reshape(-1, 20)` view the reference's plotting scripts use (plot_data.py:13-41,
+    viz_temp_varying_horizon.py:22-25): row k = [x_k(15), u_k(5)], column 14 = time, 15-18 = forces, 19 = h;
+    the missing last control is zero-padded."""
+    Z = np.asarray(Z, dtype=np.float64).reshape(-1)
+    return np.concatenate([Z, np.zeros(NU)]).reshape(N, NZK)

@@ -184,3 +184,71 @@ def test_large_batch_properties():
     jc = out["jac"][:, torch.from_numpy(const).cuda()]
     expect = torch.from_numpy(np.where((rows[const] - 30) % 15 == (cols[const] - 1) % 20, -1.0, 0.0)).cuda()
     assert bool((jc == expect).all())
+
+
+def test_c3_sweep_65536_problems_with_their_own_initial_state():
+    """256 drop heights x 256 initial pitches, per-problem x0, guesses built on the device,
+    all four outputs, then Z += 1e-3 xi for 3 'iterations'.  A strided sample is checked against the oracle."""
+    p = ql.default_problem()
+    nlp, o = ql.HybridNLP.from_problem(p), Oracle(p)
+    x0 = ql.sweep_initial_states(p.model, np.linspace(0.25, 3.0, 256), np.linspace(-40.0, -5.0, 256))
+    x0d = torch.from_numpy(x0).cuda()
+    Z = ql.initial_guess_batch(p, x0d, xp=torch)
+    assert Z.shape == (65536, 1215) and Z.is_cuda
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    sample = np.arange(0, 65536, 257)
+    out = None
+    for it in range(3):
+        out = nlp.eval_batch(Z, x0=x0d, out=out)
+        torch.cuda.synchronize()
+        Zs = Z[torch.from_numpy(sample).cuda()].cpu().numpy()
+        ref = o.eval_batch(Zs, x0=x0[sample])
+        got = {k: v[torch.from_numpy(sample).cuda()].cpu().numpy() for k, v in out.items()}
+        assert_same_bits(nlp, got, ref, f"iter {it}: ")
+        # init rows are Z[x_1] - x0 for every problem (constraints.jl:149)
+        assert bool((out["g"][:, :15] == Z[:, :15] - x0d).all())
+        Z = Z + 1e-3 * torch.randn(Z.shape, generator=gen, device="cuda", dtype=torch.float64)
+
+
+def test_c4_ragged_batch_of_mixed_horizons():
+    """(N, k_trans) in 6 classes x init_mode in {1, 2}, uniformly mixed, flat arrays + offsets."""
+    classes = [(N, kt, im) for (N, kt) in [(31, 11), (41, 14), (61, 21), (81, 27), (101, 34), (121, 41)] for im in (1, 2)]
+    probs = [ql.build_problem(N=N, k_trans=kt, init_mode=im) for N, kt, im in classes]
+    ev = ql.RaggedEvaluator(probs)
+    rng = np.random.default_rng(7)
+    B = 4096
+    class_of = rng.integers(0, len(classes), size=B)
+    off = ev.offsets(class_of)
+    guesses = [ql.initial_guess(p) for p in probs]
+    Zf = np.concatenate([guesses[c] for c in class_of]) + 1e-2 * rng.standard_normal(int(off["z_off"][-1]))
+    for b in range(B):                                     # clip the h entries like the other configs
+        seg = Zf[off["z_off"][b]:off["z_off"][b + 1]]
+        seg[19::20] = np.clip(seg[19::20], 1e-3, 2e-2)
+    out = ev.eval(class_of, torch.from_numpy(Zf).cuda())
+    torch.cuda.synchronize()
+    oracles = [Oracle(p) for p in probs]
+    for b in range(0, B, 37):
+        c = class_of[b]
+        z = Zf[off["z_off"][b]:off["z_off"][b + 1]]
+        ref = oracles[c].eval_batch(z[None, :])
+        got = {"f": out["f"][b:b + 1].cpu().numpy(),
+               "grad": out["grad"][off["z_off"][b]:off["z_off"][b + 1]].cpu().numpy()[None, :],
+               "g": out["g"][off["g_off"][b]:off["g_off"][b + 1]].cpu().numpy()[None, :],
+               "jac": out["jac"][off["j_off"][b]:off["j_off"][b + 1]].cpu().numpy()[None, :]}
+        assert_same_bits(ev.nlps[c], got, ref, f"problem {b} class {classes[c]}: ")
+
+
+def test_c5_sized_shard_131072_per_gpu():
+    """2^20 trajectories over 8 GPUs = 131,072 per GPU (33.7 GB of Jacobian values).  One shard
+    is evaluated here; the result must not depend on the position in the batch, and a sample matches the oracle."""
+    p = ql.default_problem()
+    nlp, o = ql.HybridNLP.from_problem(p), Oracle(p)
+    B = 131072
+    small = perturbed_batch(p, [ql.initial_guess(p)], 512, 5e-2, 2 ** 20)
+    Z = torch.from_numpy(small).cuda().repeat(B // 512, 1)
+    out = nlp.eval_batch(Z, want=("g", "jac"))
+    torch.cuda.synchronize()
+    jac = out["jac"].view(B // 512, 512, -1)
+    assert bool((jac[1:] == jac[:1]).all())
+    assert_same_bits(nlp, {"jac": jac[0, :64].cpu().numpy(), "g": out["g"][:64].cpu().numpy()},
+                     o.eval_batch(small[:64], want=("g", "jac")))

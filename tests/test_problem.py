@@ -45,3 +45,22 @@ def test_initial_guess_layout():
     assert np.array_equal(X[0][:14], p.x0[:14]) and np.allclose(X[20][:14], p.xf[:14], atol=1e-15)
     assert abs(X[20][14] - 0.02) < 1e-15 and abs(X[60][14] - 0.82) < 1e-13        # 20*0.001 + 40*0.02
     assert U[0][1] == 98.10000000000001
+
+
+def test_sweep_and_batched_guess_match_the_single_problem_formulas():
+    p = ql.default_problem()
+    x0 = ql.sweep_initial_states(p.model, [0.25, 2.0, 3.0], [-40.0, -30.0, -5.0])
+    assert x0.shape == (9, 15) and np.array_equal(x0[4], p.x0)                       # h=2, theta=-30 is the notebook case
+    assert x0[0][8] == -np.sqrt(2 * 9.81 * 0.25) and x0[2][2] == -5.0 * np.pi / 180  # main.ipynb:92-93,118,122
+    Z = ql.initial_guess_batch(p, x0)
+    for b in range(9):
+        assert np.array_equal(Z[b], ql.initial_guess(ql.build_problem(xinit=x0[b])))
+
+
+def test_solution_csv_round_trip(tmp_path, golden):
+    path = str(tmp_path / "z.csv")
+    ql.save_solution_csv(path, golden["data_6"])
+    assert np.array_equal(ql.load_solution_csv(path), golden["data_6"])              # writedlm / loadtxt format
+    tab = ql.solution_table(golden["data_6"], 61)
+    assert tab.shape == (61, 20) and tab[60, 14] == 0.848539898959304 and not tab[60, 15:].any()
+    assert tab[59, 16] + tab[59, 18] == 98.10000000000001                            # plot_data.py columns 15-18 = forces
