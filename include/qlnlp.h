@@ -46,8 +46,11 @@ enum {
 };
 
 enum {
-    QLNLP_JAC_SPARSE_BLOCK = 0,
-    QLNLP_JAC_DENSE = 1
+    QLNLP_JAC_SPARSE_BLOCK = 0,   /* the entries jac_c! assigns (zeros of the identity / RK4 blocks included) */
+    QLNLP_JAC_DENSE = 1,          /* the reference's full m_nlp x n_nlp grid; single evaluations only */
+    QLNLP_JAC_SPARSE_TRUE = 2     /* only structurally non-zero entries: identity blocks as diagonals, RK4 blocks
+                                     as their mode pattern (71/71/57 entries, 56 at the jump knot); 4,840 values
+                                     instead of 32,161 at the default instance, same column-major order */
 };
 
 /* planar_quadruped.jl:11-20 */
@@ -112,8 +115,10 @@ typedef struct {
     double* f;                          /* [B]                                    or NULL: skip */
     double* grad;      int64_t ldgrad;  /* [B][ldgrad], ldgrad >= n_nlp           or NULL: skip */
     double* g;         int64_t ldg;     /* [B][ldg],    ldg    >= m_nlp           or NULL: skip */
-    double* jac;       int64_t ldjac;   /* [B][ldjac],  ldjac  >= nnz_block       or NULL: skip
-                                           SPARSE_BLOCK values.  The TMA bulk-store path needs jac
+    double* jac;       int64_t ldjac;   /* [B][ldjac],  ldjac  >= nnz             or NULL: skip
+                                           values in the handle's sparse pattern (SPARSE_TRUE handles:
+                                           nnz_true; SPARSE_BLOCK and DENSE handles: nnz_block).
+                                           The TMA bulk-store path needs jac
                                            16-byte aligned and ldjac even; otherwise a slower
                                            plain-store path is used. */
 } qlnlp_batch_io;

@@ -62,6 +62,12 @@ def lib():
             getattr(L, name).argtypes = [P, dp, dp]
         L.qlo_plan_create.restype = C.c_void_p
         L.qlo_plan_create.argtypes = [P]
+        L.qlo_plan_create_true.restype = C.c_void_p
+        L.qlo_plan_create_true.argtypes = [P]
+        L.qlo_plan_nnz.restype = C.c_int64
+        L.qlo_plan_nnz.argtypes = [C.c_void_p]
+        L.qlo_plan_structure.restype = None
+        L.qlo_plan_structure.argtypes = [C.c_void_p, dp, dp]
         L.qlo_plan_destroy.restype = None
         L.qlo_plan_destroy.argtypes = [C.c_void_p]
         L.qlo_jac_c_sparse.restype = None
@@ -133,12 +139,37 @@ class Oracle:
         self.n_nlp = int(L.qlo_num_primals(self._p))
         self.m_nlp = int(L.qlo_num_duals(self._p))
         self._plan = None
+        self._plan_true = None
         self._nnz = None
 
     def __del__(self):
-        if getattr(self, "_plan", None):
-            lib().qlo_plan_destroy(self._plan)
-            self._plan = None
+        for name in ("_plan", "_plan_true"):
+            if getattr(self, name, None):
+                lib().qlo_plan_destroy(getattr(self, name))
+                setattr(self, name, None)
+
+    # --- SPARSE_TRUE pattern (structural non-zeros only)
+    @property
+    def plan_true(self):
+        if self._plan_true is None:
+            self._plan_true = lib().qlo_plan_create_true(self._p)
+        return self._plan_true
+
+    @property
+    def nnz_true(self) -> int:
+        return int(lib().qlo_plan_nnz(self.plan_true))
+
+    def jacobian_structure_true(self):
+        rows = np.empty(self.nnz_true, dtype=np.int64)
+        cols = np.empty(self.nnz_true, dtype=np.int64)
+        lib().qlo_plan_structure(self.plan_true, _ptr(rows), _ptr(cols))
+        return rows, cols
+
+    def jac_c_sparse_true(self, Z) -> np.ndarray:
+        Z = _f64(Z)
+        out = np.full(self.nnz_true, np.nan)
+        lib().qlo_jac_c_sparse(self.plan_true, self._p, _ptr(Z), _ptr(out))
+        return out
 
     @property
     def plan(self):
@@ -199,7 +230,7 @@ class Oracle:
         return xl, xu
 
     # --- batches
-    def eval_batch(self, Z, x0=None, xf=None, want=("f", "grad", "g", "jac"), nthreads: int = 0):
+    def eval_batch(self, Z, x0=None, xf=None, want=("f", "grad", "g", "jac"), nthreads: int = 0, pattern="block"):
         Z = _f64(Z)
         B = Z.shape[0]
         assert Z.shape[1] == self.n_nlp
@@ -208,10 +239,11 @@ class Oracle:
         f = np.empty(B) if "f" in want else None
         grad = np.empty((B, self.n_nlp)) if "grad" in want else None
         g = np.empty((B, self.m_nlp)) if "g" in want else None
-        jac = np.empty((B, self.nnz)) if "jac" in want else None
-        lib().qlo_eval_batch(self.plan, self._p, B, _ptr(Z), self.n_nlp, _ptr(x0), _ptr(xf),
+        plan, nnz = (self.plan, self.nnz) if pattern == "block" else (self.plan_true, self.nnz_true)
+        jac = np.empty((B, nnz)) if "jac" in want else None
+        lib().qlo_eval_batch(plan, self._p, B, _ptr(Z), self.n_nlp, _ptr(x0), _ptr(xf),
                              _ptr(f), _ptr(grad), self.n_nlp, _ptr(g), self.m_nlp,
-                             _ptr(jac), self.nnz, int(nthreads))
+                             _ptr(jac), nnz, int(nthreads))
         return {"f": f, "grad": grad, "g": g, "jac": jac}
 
     @staticmethod

@@ -495,12 +495,71 @@ typedef struct { const qlo_plan *pl; double *vals; } sparse_ctx;
 static void put_sparse(void *c, int64_t row, int64_t col, double v)
 {
     sparse_ctx *s = (sparse_ctx *)c;
-    s->vals[s->pl->lin2pos[row + s->pl->m * col]] = v;
+    const int32_t pos = s->pl->lin2pos[row + s->pl->m * col];
+    if (pos >= 0) s->vals[pos] = v;     /* SPARSE_TRUE plans drop the structural zeros jac_c! assigns */
 }
 void qlo_jac_c_sparse(const qlo_plan *pl, const qlo_problem *p, const double *Z, double *vals)
 {
     sparse_ctx c = {pl, vals};
     jac_c_assign(p, Z, put_sparse, &c);
+}
+
+/* ---- SPARSE_TRUE: the assigned entries that are not structurally zero.  Determined numerically: an entry
+ * belongs to the pattern iff it is non-zero at one of a few generic pseudo-random points (identity blocks
+ * contribute their diagonals, the RK4 blocks their mode-specific pattern, the jump knot its unmasked rows). */
+typedef struct { unsigned char *mask; int64_t m; } nzmask_ctx;
+static void put_nzmask(void *c, int64_t row, int64_t col, double v)
+{
+    nzmask_ctx *d = (nzmask_ctx *)c;
+    if (v != 0.0) d->mask[row + d->m * col] = 1;
+}
+static unsigned char *nonzero_mask(const qlo_problem *p)
+{
+    const ql_dims d = make_dims(p);
+    double *Z = (double *)malloc(sizeof(double) * (size_t)d.n_nlp);
+    nzmask_ctx c;
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    int rep;
+    int64_t i, k;
+    c.m = d.m_nlp;
+    c.mask = (unsigned char *)calloc((size_t)(d.m_nlp * d.n_nlp), 1);
+    for (rep = 0; rep < 4; ++rep) {
+        for (i = 0; i < d.n_nlp; ++i) {
+            s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+            Z[i] = 0.25 + 1.5 * (double)(s >> 11) * (1.0 / 9007199254740992.0);   /* in (0.25, 1.75): generic, theta > 0 */
+            if (s & 1) Z[i] = -Z[i];
+        }
+        for (k = 0; k < p->N - 1; ++k) Z[uind(k) + 4] = 0.003 + 0.001 * (double)rep + 1e-4 * (double)(k % 7);
+        jac_c_assign(p, Z, put_nzmask, &c);
+    }
+    free(Z);
+    return c.mask;
+}
+
+static qlo_plan *plan_from_mask(const qlo_problem *p, unsigned char *mask)
+{
+    const ql_dims d = make_dims(p);
+    qlo_plan *pl = (qlo_plan *)malloc(sizeof *pl);
+    int64_t i, n = 0;
+    pl->m = d.m_nlp;
+    pl->n = d.n_nlp;
+    pl->lin2pos = (int32_t *)malloc(sizeof(int32_t) * (size_t)(d.m_nlp * d.n_nlp));
+    for (i = 0; i < d.m_nlp * d.n_nlp; ++i) pl->lin2pos[i] = mask[i] ? (int32_t)n++ : -1;
+    pl->nnz = n;
+    free(mask);
+    return pl;
+}
+qlo_plan *qlo_plan_create_true(const qlo_problem *p) { return plan_from_mask(p, nonzero_mask(p)); }
+int64_t qlo_plan_nnz(const qlo_plan *pl) { return pl->nnz; }
+/* rows/cols (1-based, column-major) of the plan's pattern */
+void qlo_plan_structure(const qlo_plan *pl, int64_t *rows, int64_t *cols)
+{
+    int64_t r, c;
+    for (c = 0; c < pl->n; ++c)
+        for (r = 0; r < pl->m; ++r) {
+            const int32_t pos = pl->lin2pos[r + pl->m * c];
+            if (pos >= 0) { rows[pos] = r + 1; cols[pos] = c + 1; }
+        }
 }
 
 int qlo_max_threads(void)

@@ -79,6 +79,11 @@ void qlo_jacobian_structure(const qlo_problem *p, int64_t *rows, int64_t *cols);
 typedef struct qlo_plan qlo_plan;
 qlo_plan *qlo_plan_create(const qlo_problem *p);
 void qlo_plan_destroy(qlo_plan *pl);
+/* SPARSE_TRUE plan: the assigned entries that are not structurally zero (identity blocks as diagonals, RK4
+ * blocks as their mode pattern).  qlo_jac_c_sparse / qlo_eval_batch work with either kind of plan. */
+qlo_plan *qlo_plan_create_true(const qlo_problem *p);
+int64_t qlo_plan_nnz(const qlo_plan *pl);
+void qlo_plan_structure(const qlo_plan *pl, int64_t *rows, int64_t *cols);
 /* same assignments as qlo_jac_c_dense, written into vals[nnz] in structure order */
 void qlo_jac_c_sparse(const qlo_plan *pl, const qlo_problem *p, const double *Z, double *vals);
 

@@ -18,8 +18,10 @@
 
 #if defined(__CUDACC__)
 #define QL_HD __host__ __device__ __forceinline__
+#define QL_UNROLL _Pragma("unroll")
 #else
 #define QL_HD static inline
+#define QL_UNROLL
 #endif
 
 #define QL_NX 15
@@ -32,7 +34,8 @@
 
 struct QlClass {
     int N, k_trans, init_mode;            // 1-based meaning, as in HybridNLP (nlp.jl:16-19)
-    int n_nlp, m_nlp, nnz;                // nlp.jl:72,63 ; entries jac_c! assigns
+    int n_nlp, m_nlp, nnz;                // nlp.jl:72,63 ; entries jac_c! assigns (SPARSE_BLOCK)
+    int nnz_true;                         // structurally non-zero entries (SPARSE_TRUE)
     int c_term, c_dyn, c_cfirst, c_cother, c_fctrl, c_body;   // 0-based first row of each g block (c_init = 0)
     int npass;                            // ceil(N / 32)
     double g, mb, mf, lb;                 // planar_quadruped.jl:11-20
@@ -59,6 +62,7 @@ QL_HD void ql_class_init(QlClass* c, int N, int k_trans, int init_mode,
     c->Ib = mb * (lb * lb) / 12;
     c->mbg = mb * g;
     c->half_lb = lb / 2;
+    c->nnz_true = 0;                      // filled by ql_class_finish (needs the helpers below)
 }
 
 // ---- per-knot extras -----------------------------------------------------------------------
@@ -134,6 +138,41 @@ QL_HD void ql_write_run_constants(const QlClass& c, int k, double* run)
         run[cb + 15 * 3 + 1 + 15] = 1.0;                       // ... and of control column 18 (F2y)
     }
 }
+
+// ---- SPARSE_TRUE: only structurally non-zero entries (identity blocks as diagonals, RK4 blocks as their
+// mode-specific pattern: 71 / 71 / 57 entries for modes 1 / 2 / 3, 56 at the jump knot) ------------------
+// run length of a knot without its extras; the per-mode counts come from rk4_dual_gen.h (QL_TRUE_LEN_*):
+//   86 = 15 diagonal + 71 pattern (initial mode), 71 = 15 + 56 (jump knot), 72 = 15 + 57 (mode 3)
+#define QL_TRUE_LEN_INIT 86
+#define QL_TRUE_LEN_JUMPK 71
+#define QL_TRUE_LEN_M3 72
+#define QL_TRUE_LEN_LAST 29      // knot N: 14 term-diagonal + 15 (-I)-diagonal entries
+#define QL_TRUE_PBUF 2948        // doubles of the per-pass staging buffer: 32 x (86 + 6) + parity, rounded to 16 B
+
+QL_HD int ql_true_base_len(const QlClass& c, int k)
+{
+    if (k == c.N) return QL_TRUE_LEN_LAST;
+    if (k >= c.k_trans) return QL_TRUE_LEN_M3;
+    return k == c.k_trans - 1 ? QL_TRUE_LEN_JUMPK : QL_TRUE_LEN_INIT;
+}
+// offset of knot k's run in the SPARSE_TRUE value stream
+QL_HD int ql_true_run_off(const QlClass& c, int k)
+{
+    const int km = k - 1;                                                // knots before k
+    const int kj = c.k_trans - 1;                                        // the jump knot (0: none)
+    int n_init = kj - 1; if (n_init < 0) n_init = 0; if (n_init > km) n_init = km;
+    const int n_jump = (kj >= 1 && kj <= km) ? 1 : 0;
+    int hi = km < c.N - 1 ? km : c.N - 1;
+    int n_m3 = hi - c.k_trans + 1; if (n_m3 < 0) n_m3 = 0;
+    int o = n_init * QL_TRUE_LEN_INIT + n_jump * QL_TRUE_LEN_JUMPK + n_m3 * QL_TRUE_LEN_M3;
+    o += 3 * km;                                                         // body-pos x2 + contact-first per knot
+    if (k > c.k_trans) o += k - c.k_trans;                               // contact-other entries
+    if (k == c.N) o += 2;                                                // final-ctrl entries of knot N-1
+    return o;
+}
+QL_HD int ql_true_nnz(const QlClass& c) { return ql_true_run_off(c, c.N) + QL_TRUE_LEN_LAST + 2 + ql_e4(c, c.N) + ql_e6(c, c.N); }
+
+QL_HD void ql_class_finish(QlClass* c) { c->nnz_true = ql_true_nnz(*c); }
 
 // ---- segments: what one bulk store moves ---------------------------------------------------
 // A segment is 1 or 2 consecutive knots of one pass.  Its image lives in a staging buffer at offset

@@ -67,8 +67,8 @@ struct qlnlp_handle_s {
     long long* d_dense_lin = nullptr;  // DENSE mode: linear index of every SPARSE_BLOCK value
     double* d_dense = nullptr;         // DENSE mode: m x n grid
     int sm_count = 0;
-    int blocks_per_sm[2] = {0, 0};     // [with_jac]
-    size_t smem[2] = {0, 0};
+    int blocks_per_sm[3] = {0, 0, 0};  // [JM_NONE, JM_BLOCK, JM_TRUE]
+    size_t smem[3] = {0, 0, 0};
     double rmb = 0, rmf = 0, rIb = 0;  // reciprocals of the divisors
     bool fastdiv = false;              // reciprocal-FMA division verified exact for this model
     int64_t last_launch[5] = {0, 0, 0, 0, 0};
@@ -160,10 +160,46 @@ bool fastdiv_is_exact(double b)
     return true;
 }
 
-const void* kernel_fn(bool with_jac, bool fast)
+const void* kernel_fn(int jm, bool fast)
 {
-    if (with_jac) return fast ? (const void*)ql::eval_kernel<true, true> : (const void*)ql::eval_kernel<true, false>;
-    return fast ? (const void*)ql::eval_kernel<false, true> : (const void*)ql::eval_kernel<false, false>;
+    if (jm == ql::JM_BLOCK) return fast ? (const void*)ql::eval_kernel<ql::JM_BLOCK, true> : (const void*)ql::eval_kernel<ql::JM_BLOCK, false>;
+    if (jm == ql::JM_TRUE) return fast ? (const void*)ql::eval_kernel<ql::JM_TRUE, true> : (const void*)ql::eval_kernel<ql::JM_TRUE, false>;
+    return fast ? (const void*)ql::eval_kernel<ql::JM_NONE, true> : (const void*)ql::eval_kernel<ql::JM_NONE, false>;
+}
+
+// the sparse pattern batched evaluations of this handle produce (DENSE handles batch in SPARSE_BLOCK)
+int batch_jm(qlnlp_handle h);
+int batch_nnz(qlnlp_handle h);
+
+// SPARSE_TRUE structure (1-based, value order): like sparse_block_structure restricted to structural non-zeros
+void sparse_true_structure(const QlClass& c, int64_t* rows, int64_t* cols)
+{
+    int64_t n = 0;
+    for (int k = 1; k <= c.N; ++k) {
+        const int ncol = (k < c.N) ? QL_NZK : QL_NX;
+        const int mode = (k >= c.k_trans) ? 3 : c.init_mode;
+        const QlTruePattern pat = ql_true_pattern(mode, k < c.N && k == c.k_trans - 1);
+        for (int j = 0; j < ncol; ++j) {
+            const int64_t col = (int64_t)QL_NZK * (k - 1) + j + 1;
+            auto put = [&](int64_t row0) { rows[n] = row0 + 1; cols[n] = col; ++n; };
+            if (j < QL_NX) {
+                if (k == 1) put(j);                                              // init diagonal
+                if (k == c.N && j < QL_NX - 1) put(c.c_term + j);                // term diagonal
+                if (k >= 2) put(c.c_dyn + QL_NX * (k - 2) + j);                  // -I diagonal
+            }
+            if (k < c.N)
+                for (int e = 0; e < pat.n; ++e)
+                    if (pat.J[e] == j) put(c.c_dyn + QL_NX * (k - 1) + pat.I[e]);
+            if (j < QL_NX) {
+                const int jf = (c.init_mode == 1) ? 4 : 6, jo = (c.init_mode == 1) ? 6 : 4;
+                if (j == jf) put(c.c_cfirst + (k - 1));
+                if (j == jo && k >= c.k_trans) put(c.c_cother + (k - c.k_trans));
+                if (j == 1 || j == 2) put(c.c_body + (k - 1));
+            } else if (k == c.N - 1 && (j == 16 || j == 18)) {
+                put(c.c_fctrl);
+            }
+        }
+    }
 }
 
 int check_handle(qlnlp_handle h)
@@ -202,12 +238,12 @@ int ensure_device(qlnlp_handle h)
     CUDA_TRY(cudaMalloc(&h->d_seg_begin, h->seg_begin.size() * sizeof(int)));
     CUDA_TRY(cudaMemcpy(h->d_seg_begin, h->seg_begin.data(), h->seg_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
 
-    for (int wj = 0; wj < 2; ++wj) {
-        h->smem[wj] = ql::smem_bytes(h->cls.N, wj != 0);
+    for (int wj = 0; wj < 3; ++wj) {
+        h->smem[wj] = ql::smem_bytes(h->cls.N, wj);
         if (h->smem[wj] > (size_t)prop.sharedMemPerBlockOptin)
             return fail(QLNLP_EINVAL, "N=%d needs %zu B of shared memory per warp (> %zu)", h->cls.N, h->smem[wj],
                         (size_t)prop.sharedMemPerBlockOptin);
-        const void* fn = kernel_fn(wj != 0, h->fastdiv);
+        const void* fn = kernel_fn(wj, h->fastdiv);
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem[wj]));
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int nb = 0;
@@ -228,7 +264,7 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     if (io->ldz < c.n_nlp) return fail(QLNLP_EINVAL, "ldz %lld < n_nlp %d", (long long)io->ldz, c.n_nlp);
     if (io->grad && io->ldgrad < c.n_nlp) return fail(QLNLP_EINVAL, "ldgrad %lld < n_nlp %d", (long long)io->ldgrad, c.n_nlp);
     if (io->g && io->ldg < c.m_nlp) return fail(QLNLP_EINVAL, "ldg %lld < m_nlp %d", (long long)io->ldg, c.m_nlp);
-    if (io->jac && io->ldjac < c.nnz) return fail(QLNLP_EINVAL, "ldjac %lld < nnz %d", (long long)io->ldjac, c.nnz);
+    if (io->jac && io->ldjac < batch_nnz(h)) return fail(QLNLP_EINVAL, "ldjac %lld < nnz %d", (long long)io->ldjac, batch_nnz(h));
     if ((reinterpret_cast<uintptr_t>(io->Z) & 7) != 0) return fail(QLNLP_EINVAL, "Z must be 8-byte aligned");
     if (B == 0) return QLNLP_OK;
 
@@ -252,11 +288,11 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     P.bulk = (io->jac && (reinterpret_cast<uintptr_t>(io->jac) & 15) == 0 && (io->ldjac & 1) == 0) ? 1 : 0;
     P.zbulk = ((reinterpret_cast<uintptr_t>(io->Z) & 15) == 0 && (io->ldz & 1) == 0) ? 1 : 0;   // ldz even > n_nlp (odd)
 
-    const int wj = io->jac ? 1 : 0;
+    const int wj = io->jac ? batch_jm(h) : ql::JM_NONE;
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm[wj];
     const int grid = (int)std::min<int64_t>(B, resident);
     void* args[] = {&P};
-    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj != 0, h->fastdiv), dim3(grid), dim3(QL_LANES), args, h->smem[wj], stream));
+    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj, h->fastdiv), dim3(grid), dim3(QL_LANES), args, h->smem[wj], stream));
     h->last_launch[0] = grid;
     h->last_launch[1] = QL_LANES;
     h->last_launch[2] = (int64_t)h->smem[wj];
@@ -280,7 +316,7 @@ int reserve_lane(qlnlp_handle h, HostLane& ln, int64_t cap)
     h->ldz_e = (c.n_nlp + 1) & ~1;
     h->ldgrad_e = h->ldz_e;
     h->ldg_e = (c.m_nlp + 1) & ~1;
-    h->ldjac_e = (c.nnz + 1) & ~1;
+    h->ldjac_e = (batch_nnz(h) + 1) & ~1;
     CUDA_TRY(cudaMalloc(&ln.Z, sizeof(double) * cap * h->ldz_e));
     CUDA_TRY(cudaMalloc(&ln.x0, sizeof(double) * cap * QL_NX));
     CUDA_TRY(cudaMalloc(&ln.xf, sizeof(double) * cap * QL_NX));
@@ -310,7 +346,7 @@ int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
     if (io->ldz < c.n_nlp) return fail(QLNLP_EINVAL, "ldz < n_nlp");
     if (io->grad && io->ldgrad < c.n_nlp) return fail(QLNLP_EINVAL, "ldgrad < n_nlp");
     if (io->g && io->ldg < c.m_nlp) return fail(QLNLP_EINVAL, "ldg < m_nlp");
-    if (io->jac && io->ldjac < c.nnz) return fail(QLNLP_EINVAL, "ldjac < nnz");
+    if (io->jac && io->ldjac < batch_nnz(h)) return fail(QLNLP_EINVAL, "ldjac < nnz");
     if (B <= 0) return B == 0 ? QLNLP_OK : fail(QLNLP_EINVAL, "negative batch");
     const int64_t chunk = std::min<int64_t>(B, HOST_CHUNK);
     const int nlanes = (B > chunk) ? 2 : 1;
@@ -340,11 +376,14 @@ int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
         if (io->f) CUDA_TRY(cudaMemcpyAsync(io->f + b0, ln.f, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
         if (io->grad) CUDA_TRY(copy_rows(io->grad + b0 * io->ldgrad, io->ldgrad, ln.grad, h->ldgrad_e, c.n_nlp, nb, cudaMemcpyDeviceToHost, s));
         if (io->g) CUDA_TRY(copy_rows(io->g + b0 * io->ldg, io->ldg, ln.g, h->ldg_e, c.m_nlp, nb, cudaMemcpyDeviceToHost, s));
-        if (io->jac) CUDA_TRY(copy_rows(io->jac + b0 * io->ldjac, io->ldjac, ln.jac, h->ldjac_e, c.nnz, nb, cudaMemcpyDeviceToHost, s));
+        if (io->jac) CUDA_TRY(copy_rows(io->jac + b0 * io->ldjac, io->ldjac, ln.jac, h->ldjac_e, batch_nnz(h), nb, cudaMemcpyDeviceToHost, s));
     }
     for (int l = 0; l < nlanes; ++l) CUDA_TRY(cudaStreamSynchronize(h->lanes[l].stream));
     return QLNLP_OK;
 }
+
+int batch_jm(qlnlp_handle h) { return h->jac_mode == QLNLP_JAC_SPARSE_TRUE ? ql::JM_TRUE : ql::JM_BLOCK; }
+int batch_nnz(qlnlp_handle h) { return h->jac_mode == QLNLP_JAC_SPARSE_TRUE ? h->cls.nnz_true : h->cls.nnz; }
 
 }  // namespace
 
@@ -362,11 +401,12 @@ int qlnlp_create(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_ha
     if (d->N < 2 || d->N > QL_MAX_N) return fail(QLNLP_EINVAL, "N=%lld outside [2, 1024]", (long long)d->N);
     if (d->k_trans < 1 || d->k_trans > d->N) return fail(QLNLP_EINVAL, "k_trans=%lld outside [1, N]", (long long)d->k_trans);
     if (d->init_mode != 1 && d->init_mode != 2) return fail(QLNLP_EINVAL, "init_mode must be 1 or 2");
-    if (jac_mode != QLNLP_JAC_SPARSE_BLOCK && jac_mode != QLNLP_JAC_DENSE) return fail(QLNLP_EINVAL, "unknown jac_mode %d", jac_mode);
+    if (jac_mode != QLNLP_JAC_SPARSE_BLOCK && jac_mode != QLNLP_JAC_DENSE && jac_mode != QLNLP_JAC_SPARSE_TRUE) return fail(QLNLP_EINVAL, "unknown jac_mode %d", jac_mode);
     if (!d->Q || !d->R || !d->q || !d->r || !d->c) return fail(QLNLP_EINVAL, "cost tables are required");
     qlnlp_handle h = new (std::nothrow) qlnlp_handle_s();
     if (!h) return fail(QLNLP_ENOMEM, "out of host memory");
     ql_class_init(&h->cls, (int)d->N, (int)d->k_trans, (int)d->init_mode, d->model.g, d->model.mb, d->model.mf, d->model.lb);
+    ql_class_finish(&h->cls);
     h->device = device;
     h->jac_mode = jac_mode;
     std::memcpy(h->x0, d->x0, sizeof h->x0);
@@ -417,7 +457,7 @@ int qlnlp_dims(qlnlp_handle h, int64_t* n_nlp, int64_t* m_nlp, int64_t* nnz, int
     if (int rc = check_handle(h)) return rc;
     if (n_nlp) *n_nlp = h->cls.n_nlp;
     if (m_nlp) *m_nlp = h->cls.m_nlp;
-    if (nnz) *nnz = (h->jac_mode == QLNLP_JAC_DENSE) ? (int64_t)h->cls.m_nlp * h->cls.n_nlp : h->cls.nnz;
+    if (nnz) *nnz = (h->jac_mode == QLNLP_JAC_DENSE) ? (int64_t)h->cls.m_nlp * h->cls.n_nlp : batch_nnz(h);
     if (nnz_block) *nnz_block = h->cls.nnz;
     return QLNLP_OK;
 }
@@ -431,6 +471,8 @@ int qlnlp_jacobian_structure(qlnlp_handle h, int64_t* rows, int64_t* cols)
         int64_t n = 0;
         for (int64_t col = 1; col <= h->cls.n_nlp; ++col)
             for (int64_t row = 1; row <= h->cls.m_nlp; ++row) { rows[n] = row; cols[n] = col; ++n; }
+    } else if (h->jac_mode == QLNLP_JAC_SPARSE_TRUE) {
+        sparse_true_structure(h->cls, rows, cols);
     } else {
         sparse_block_structure(h->cls, rows, cols);
     }
@@ -491,7 +533,7 @@ static int eval_one(qlnlp_handle h, const double* x, double* f, double* grad, do
     io.f = f;
     io.grad = grad; io.ldgrad = h->cls.n_nlp;
     io.g = g; io.ldg = h->cls.m_nlp;
-    io.jac = jac; io.ldjac = h->cls.nnz;
+    io.jac = jac; io.ldjac = batch_nnz(h);
     return eval_host(h, 1, &io);
 }
 
@@ -517,7 +559,7 @@ int qlnlp_eval_constraint_jacobian(qlnlp_handle h, const double* x, double* vals
 {
     if (int rc = check_handle(h)) return rc;
     if (!vals) return fail(QLNLP_EINVAL, "null output");
-    if (h->jac_mode == QLNLP_JAC_SPARSE_BLOCK) return eval_one(h, x, nullptr, nullptr, nullptr, vals);
+    if (h->jac_mode != QLNLP_JAC_DENSE) return eval_one(h, x, nullptr, nullptr, nullptr, vals);
 
     // DENSE: evaluate SPARSE_BLOCK on the device, scatter into the zeroed m x n grid, copy back
     if (!x) return fail(QLNLP_EINVAL, "null x");

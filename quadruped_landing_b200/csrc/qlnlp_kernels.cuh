@@ -17,6 +17,9 @@
 //      shared-memory image whose constants persist from one evaluation to the next; the owner
 //      lanes patch only the value-dependent entries and one lane fires a TMA bulk store
 //      (cp.async.bulk.global.shared::cta, SASS UBLKCP) of the whole 4-8 KB segment.
+// With the SPARSE_TRUE pattern (JM == 2: only structural non-zeros, 4,840 instead of 32,161 values) there are no
+// zeros to persist: every lane writes its knot's whole run into a per-pass staging buffer and the pass goes
+// out as one bulk store.
 // All arithmetic is fp64 with explicit round-to-nearest add/mul/div (no FMA contraction) in the
 // reference's operation order, so g, grad and the Jacobian values are bit-identical to the CPU
 // oracle (sin/cos aside); only the cost reduction order (warp tree vs. sequential) differs.
@@ -123,7 +126,9 @@ struct Consts {
 #define QL_DIV_SIX(a) K.div_six(a)
 #define QL_FN __device__ __forceinline__
 #define QL_ST(ptr, off, val) ql::st_shared_f64((ptr) + 8u * (off), (val))
+#define QL_PADD(ptr, n) ((ptr) + 8u * (n))
 #include "rk4_dual_gen.h"
+#include "true_run.h"
 
 namespace ql {
 
@@ -153,10 +158,14 @@ struct Launch {
 
 // shared memory carve-up: staged Z (same layout as in HBM) | mbarrier | two J staging buffers | segment plan
 __host__ __device__ inline int zbuf_len(int N) { return QL_NZK * N + 2; }     // n_nlp + 1 rounded up to even, + mbarrier
-__host__ __device__ inline size_t smem_bytes(int N, bool with_jac)
+enum { JM_NONE = 0, JM_BLOCK = 1, JM_TRUE = 2 };     // which Jacobian value stream the kernel produces
+__host__ __device__ inline size_t smem_bytes(int N, int jm)
 {
     const int nseg_max = (N + 1) / 2 + (N + QL_LANES - 1) / QL_LANES;
-    return sizeof(double) * (size_t)zbuf_len(N) + (with_jac ? sizeof(double) * 2 * QL_JBUF + sizeof(QlSeg) * nseg_max : 0);
+    size_t b = sizeof(double) * (size_t)zbuf_len(N);
+    if (jm == JM_BLOCK) b += sizeof(double) * 2 * QL_JBUF + sizeof(QlSeg) * nseg_max;
+    if (jm == JM_TRUE) b += sizeof(double) * QL_TRUE_PBUF;
+    return b;
 }
 
 // Start fetching a decision vector into shared memory.  zbulk: one TMA bulk load of n+1 doubles (n is odd, the
@@ -174,9 +183,10 @@ __device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigne
     }
 }
 
-template <bool WITH_JAC, bool FASTDIV>
+template <int JM, bool FASTDIV>
 __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant__ Launch P)
 {
+    constexpr bool WITH_JAC = JM != JM_NONE;
     extern __shared__ __align__(16) double smem[];
     const QlClass& c = P.c;
     const int lane = threadIdx.x;
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
     }
     long long b = blockIdx.x;
     if (b < P.B) stage_z(P.Z + b * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
-    if (WITH_JAC) {
+    if (JM == JM_BLOCK) {
         // the segment plan lives in shared memory: one 16-byte record per segment
         const int4* src = reinterpret_cast<const int4*>(P.segs);
         int4* dst = reinterpret_cast<int4*>(plan);
@@ -346,8 +356,35 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
                 if (nb < P.B) stage_z(P.Z + nb * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
             }
 
-            // ---- 5. stream this pass's share of the Jacobian values
-            if (WITH_JAC) {
+            // ---- 5'. SPARSE_TRUE: every lane writes its whole run, the pass leaves as one bulk store
+            if (JM == JM_TRUE) {
+                double* const jrow = P.jac + b * P.ldjac;
+                const int k_first = p * QL_LANES + 1, k_end = min(c.N, k_first + QL_LANES - 1) + 1;
+                const int start = ql_true_run_off(c, k_first);
+                const int end = (k_end > c.N) ? c.nnz_true : ql_true_run_off(c, k_end);
+                const int base = start & ~1;
+                if (P.bulk && lane == 0) bulk_wait_read<0>();       // the previous pass's store has read the buffer
+                __syncwarp();
+                if (act) ql_true_write_run(c, k, jv, jtheta, jaddr + 8u * (unsigned)(ql_true_run_off(c, k) - base));
+                if (P.bulk) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    const int a = (start + 1) & ~1, e = end & ~1;
+                    if (lane == 0) {
+                        if (e > a) bulk_store(jrow + a, jaddr + 8u * (unsigned)(a - base), 8u * (unsigned)(e - a));
+                        bulk_commit();
+                    }
+                    if (lane == 1 && (start & 1)) jrow[start] = jb[start - base];
+                    if (lane == 2 && (end & 1)) jrow[end - 1] = jb[end - 1 - base];
+                } else {
+                    __syncwarp();
+                    for (int i = lane; i < end - start; i += QL_LANES) jrow[start + i] = jb[start - base + i];
+                    __syncwarp();
+                }
+            }
+
+            // ---- 5. SPARSE_BLOCK: stream this pass's share of the Jacobian values
+            if (JM == JM_BLOCK) {
                 double* const jrow = P.jac + b * P.ldjac;
                 const int roff = act ? ql_run_off(c, k) : 0;
                 const int e4 = ql_e4(c, k), e6 = ql_e6(c, k), fc = ql_fc(c, k);

@@ -36,8 +36,9 @@ def _compile_native(name):
     out_dir = os.path.join(ROOT, "tests", "native", "_build")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, name + ".so")
-    deps = [src, os.path.join(ROOT, "quadruped_landing_b200", "csrc", "layout.h"),
-            os.path.join(ROOT, "quadruped_landing_b200", "csrc", "rk4_dual_gen.h")]
+    csrc = os.path.join(ROOT, "quadruped_landing_b200", "csrc")
+    deps = [src, os.path.join(ROOT, "tests", "native", "host_consts.h")] + \
+           [os.path.join(csrc, h) for h in ("layout.h", "rk4_dual_gen.h", "true_run.h")]
     if (not os.path.exists(out)) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, src], check=True)
     return out
@@ -58,6 +59,7 @@ def emul_lib():
     import ctypes as C
     L = C.CDLL(_compile_native("emul_host"))
     L.emul_jac_stream.argtypes = [C.c_int] * 3 + [C.c_double] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.emul_true_stream.argtypes = [C.c_int] * 3 + [C.c_double] * 4 + [C.c_void_p, C.c_void_p, C.c_int]
     L.emul_run_off.argtypes = [C.c_int] * 4
     L.emul_rk4_pos.argtypes = [C.c_int] * 6
     return L

@@ -10,6 +10,7 @@
 #include "host_consts.h"
 #include "../../quadruped_landing_b200/csrc/layout.h"
 #include "../../quadruped_landing_b200/csrc/rk4_dual_gen.h"
+#include "../../quadruped_landing_b200/csrc/true_run.h"
 
 extern "C" {
 
@@ -66,6 +67,35 @@ int emul_jac_stream(int N, int k_trans, int init_mode, double g, double mb, doub
             }
             for (int i = start; i < end; ++i) out[i] = buf[i - base];
         }
+    }
+    return 0;
+}
+
+// SPARSE_TRUE stream exactly as the kernel assembles it: every knot writes its whole run at ql_true_run_off.
+int emul_true_stream(int N, int k_trans, int init_mode, double g, double mb, double mf, double lb,
+                     const double* Z, double* out, int nout)
+{
+    QlClass c;
+    ql_class_init(&c, N, k_trans, init_mode, g, mb, mf, lb);
+    ql_class_finish(&c);
+    if (nout != c.nnz_true) return -1;
+    const HostConsts K{c.g, c.mb, c.mf, c.Ib};
+    for (int i = 0; i < nout; ++i) out[i] = NAN;
+    for (int k = 1; k <= N; ++k) {
+        const double* x = Z + 20 * (k - 1);
+        double xn[15], jv[QL_NJ_MODE1];
+        if (k < N) {
+            const double* u = x + 15;
+            if (k >= k_trans) ql_rk4_jac_mode3(x, u, K, xn, jv);
+            else if (init_mode == 1) ql_rk4_jac_mode1(x, u, K, xn, jv);
+            else ql_rk4_jac_mode2(x, u, K, xn, jv);
+        }
+        const double th = x[2];
+        const double jtheta = (th > 0) ? (-c.half_lb) * std::cos(th) : c.half_lb * std::cos(th);
+        const int off = ql_true_run_off(c, k);
+        const int len = (k == N ? c.nnz_true : ql_true_run_off(c, k + 1)) - off;
+        if (off < 0 || off + len > nout) return -2;
+        ql_true_write_run(c, k, jv, jtheta, out + off);
     }
     return 0;
 }

@@ -10,6 +10,7 @@
 #define QL_DIV_SIX(a) ((a) / 6.0)
 #define QL_FN static inline
 #define QL_ST(ptr, off, val) ((ptr)[(off)] = (val))
+#define QL_PADD(ptr, n) ((ptr) + (n))
 struct HostConsts {
     double g, mb, mf, Ib;
 };

@@ -35,7 +35,7 @@ def assert_same_bits(nlp, got, ref, what=""):
             trig = np.zeros(nlp.m_nlp, dtype=bool)
             trig[nlp.m_nlp - N:] = True
         elif k == "jac":
-            rows, cols = nlp.jacobian_structure_arrays() if nlp.use_sparse_jacobian else (None, None)
+            rows, cols = nlp.jacobian_structure_arrays()        # of the handle's sparse pattern
             trig = (rows > nlp.m_nlp - N) & ((cols - 1) % 20 == 2)
         else:
             trig = np.zeros(nlp.n_nlp, dtype=bool)
@@ -252,3 +252,47 @@ def test_c5_sized_shard_131072_per_gpu():
     assert bool((jac[1:] == jac[:1]).all())
     assert_same_bits(nlp, {"jac": jac[0, :64].cpu().numpy(), "g": out["g"][:64].cpu().numpy()},
                      o.eval_batch(small[:64], want=("g", "jac")))
+
+
+@pytest.mark.parametrize("N,kt,im", [(61, 21, 1), (33, 33, 2), (5, 2, 1), (64, 2, 2)])
+def test_no_write_outside_the_rows(N, kt, im):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with canaries: every output
+    row is padded (ld > width) and surrounded by guard rows filled with a sentinel that must survive."""
+    p = ql.build_problem(N=N, k_trans=kt, init_mode=im)
+    nlp = ql.HybridNLP.from_problem(p)
+    B, guard, sentinel = 37, 3, -7.25
+    Z = perturbed_batch(p, [ql.initial_guess(p) if kt > 1 else np.zeros(p.n_nlp)], B, 1e-2, 5)
+    widths = {"grad": nlp.n_nlp, "g": nlp.m_nlp, "jac": nlp.nnz_block}
+    for pad in (2, 3):                                     # even ld (TMA path when width is even too) and odd ld
+        big, views = {}, {}
+        for k, w in widths.items():
+            big[k] = torch.full((B + 2 * guard, w + pad), sentinel, dtype=torch.float64, device="cuda")
+            views[k] = big[k][guard:guard + B, :w]
+        fbig = torch.full((B + 2 * guard,), sentinel, dtype=torch.float64, device="cuda")
+        views["f"] = fbig[guard:guard + B]
+        out = nlp.eval_batch(torch.from_numpy(Z).cuda(), out=dict(views))
+        torch.cuda.synchronize()
+        for k, w in widths.items():
+            assert bool((big[k][:guard] == sentinel).all()) and bool((big[k][guard + B:] == sentinel).all()), k
+            assert bool((big[k][:, w:] == sentinel).all()), k
+            assert not bool((out[k] == sentinel).any()), k
+        assert bool((fbig[:guard] == sentinel).all()) and bool((fbig[guard + B:] == sentinel).all())
+
+
+@pytest.mark.parametrize("N,kt,im,B", [(61, 21, 1, 2048), (61, 21, 2, 300), (31, 11, 1, 300), (121, 41, 2, 300),
+                                       (2, 1, 1, 40), (3, 2, 2, 40), (33, 33, 1, 100), (33, 1, 2, 100), (65, 2, 2, 100)])
+def test_sparse_true_pattern(N, kt, im, B):
+    """QLNLP_JAC_SPARSE_TRUE: only structural non-zeros (4,840 values at the default instance)."""
+    p = ql.build_problem(N=N, k_trans=kt, init_mode=im)
+    nlp, o = ql.HybridNLP.from_problem(p, pattern="true"), Oracle(p)
+    base = ql.initial_guess(p) if kt > 1 else np.zeros(p.n_nlp)
+    Z = perturbed_batch(p, [base], B, 1e-2, 21)
+    got = _dev_eval(nlp, Z)
+    ref = o.eval_batch(Z, pattern="true")
+    assert got["jac"].shape == (B, o.nnz_true)
+    assert_same_bits(nlp, got, ref)
+    host = nlp.eval_batch_host(Z[:17])
+    assert_same_bits(nlp, host, {k: v[:17] for k, v in ref.items()})
+    vals = np.empty(nlp.nnz)
+    nlp.eval_constraint_jacobian(vals, Z[0])                      # the MOI callback in SPARSE_TRUE order
+    assert_same_bits(nlp, {"jac": vals}, {"jac": ref["jac"][0]})

@@ -61,3 +61,37 @@ def test_segment_plan_and_value_positions(emul_lib, N, kt, im):
     assert rc == 0
     ref = Oracle(prob).jac_c_sparse(Z)
     assert np.array_equal(out, ref)          # bit-exact, including with persisted templates (2nd repetition)
+
+
+@pytest.mark.parametrize("N,kt,im", CLASSES)
+def test_sparse_true_structure_and_stream(emul_lib, N, kt, im):
+    """SPARSE_TRUE: closed-form structure == the oracle's numerically determined non-zero pattern, and the run
+    writer the kernel uses (csrc/true_run.h) reproduces the oracle's values bit for bit."""
+    prob = build_problem(N=N, k_trans=kt, init_mode=im)
+    nlp = HybridNLP.from_problem(prob, pattern="true")
+    o = Oracle(prob)
+    assert nlp.nnz == o.nnz_true == nlp.nnz_batch and nlp.nnz_block == o.nnz
+    r, c = nlp.jacobian_structure_arrays()
+    r0, c0 = o.jacobian_structure_true()
+    assert np.array_equal(r, r0) and np.array_equal(c, c0)
+    # it is a sub-sequence of SPARSE_BLOCK in the same (column-major) order
+    rb, cb = o.jacobian_structure()
+    lin, linb = (c - 1) * o.m_nlp + r, (cb - 1) * o.m_nlp + rb
+    assert np.all(np.diff(lin) > 0) and np.isin(lin, linb).all()
+    Z = _z(prob, 3 * N + kt)
+    out = np.empty(o.nnz_true)
+    m = prob.model
+    assert emul_lib.emul_true_stream(N, kt, im, m.g, m.mb, m.mf, m.lb, Z.ctypes.data, out.ctypes.data, o.nnz_true) == 0
+    assert np.array_equal(out, o.jac_c_sparse_true(Z))
+    # and equals the SPARSE_BLOCK values at those positions; everything SPARSE_BLOCK adds is exactly zero
+    vb = o.jac_c_sparse(Z)
+    sel = np.isin(linb, lin)
+    assert np.array_equal(vb[sel], out) and not vb[~sel].any()
+
+
+def test_default_instance_true_pattern_count():
+    """15 + 71 pattern entries + extras per initial-mode knot, 56 pattern entries at the jump knot, 57 in mode 3:
+    4,840 structural non-zeros at the default instance (SURVEY.md 8a quotes 4,842 / 58; the jump mask removes
+    15 of the 71 entries, not 13 -- checked against the oracle above)."""
+    nlp = HybridNLP.from_problem(build_problem(), pattern="true")
+    assert nlp.nnz == 4840

@@ -392,6 +392,51 @@ def main():
             w(f"    QL_ST(p[{col_group(j)}], {rk4_offset(i, j)}, {val});")
         w("}")
         w("")
+        # ---- SPARSE_TRUE: only the structurally non-zero entries, identity blocks as diagonals ---------------
+        # Run of a knot k < N in SPARSE_TRUE order: state column j = [diag entry] [pattern rows of column j]
+        # [extras], control column j = [pattern rows] [final-ctrl extra].  Offsets below exclude the extras;
+        # the group pointers p[grp] add them exactly as for SPARSE_BLOCK (same column groups).
+        for jump in ((0, 1) if mode != 3 else (0,)):
+            pj = [(i, j) for (i, j) in pat if not (jump and not keep[i])]
+            npat = [sum(1 for (_, jj) in pj if jj == j) for j in range(NP)]
+            base = []
+            acc = 0
+            for j in range(NP):
+                base.append(acc)
+                acc += (1 if j < NX else 0) + npat[j]
+            tag = f"MODE{mode}" + ("_JUMP" if jump else "")
+            fn = f"mode{mode}" + ("_jump" if jump else "")
+            w(f"// SPARSE_TRUE, {tag}: {len(pj)} pattern entries; run length without extras = {acc}")
+            w(f"#define QL_TRUE_NPAT_{tag} {len(pj)}")
+            w(f"#define QL_TRUE_LEN_{tag} {acc}")
+            w(f"// offset (without extras) just past column j's entries = where column j's extra row goes")
+            w(f"static const unsigned short QL_TRUE_COLEND_{tag}[{NP}] = {{{', '.join(str(base[j] + (1 if j < NX else 0) + npat[j]) for j in range(NP))}}};")
+            colend = [base[j] + (1 if j < NX else 0) + npat[j] for j in range(NP)]
+            for j in (1, 2, 4, 6, 16, 18):
+                w(f"#define QL_TRUE_X{j}_{tag} {colend[j]}")
+            w(f"static const unsigned char QL_TRUE_I_{tag}[{len(pj)}] = {{{', '.join(str(i) for i, _ in pj)}}};")
+            w(f"static const unsigned char QL_TRUE_J_{tag}[{len(pj)}] = {{{', '.join(str(j) for _, j in pj)}}};")
+            w(f"// writes the 15 diagonal entries (value dg: +1 for the init block of knot 1, -1 otherwise) and every")
+            w(f"// pattern entry of the RK4 block (jv = value-dependent entries, constants inline)")
+            w(f"template <typename PTR>")
+            w(f"QL_FN void ql_store_true_{fn}(const double* jv, const PTR* p, double dg)")
+            w("{")
+            for j in range(NX):
+                w(f"    QL_ST(p[{col_group(j)}], {base[j]}, dg);")
+            vidx = {e: n for n, e in enumerate(var)}
+            for j in range(NP):
+                r = 0
+                for (i, jj) in pj:
+                    if jj != j:
+                        continue
+                    off = base[j] + (1 if j < NX else 0) + r
+                    r += 1
+                    if (i, j) in vidx:
+                        w(f"    QL_ST(p[{col_group(j)}], {off}, jv[{vidx[(i, j)]}]);")
+                    else:
+                        w(f"    QL_ST(p[{col_group(j)}], {off}, {repr(g.cval(xn[i].part(j)))});")
+            w("}")
+            w("")
         summary.append((mode, "jac", cnt, len(var), len(con)))
     text = "\n".join(out) + "\n"
     with open(OUT, "w") as f:
