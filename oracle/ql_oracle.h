@@ -13,7 +13,7 @@
  * last printed digit -- see tests/test_oracle_kat.py).  grad_f and jac_c are
  * "parity unpinned": nothing in the reference pins their values numerically
  * and Julia is not installed, so they are pinned only by the source text and by
- * an independent extended-precision derivative (oracle/hp_check.py).
+ * an independent extended-precision derivative (tests/test_oracle_hp.py).
  *
  * Arithmetic rules reproduced (all IEEE fp64, no FMA contraction; compile with
  * -ffp-contract=off):
