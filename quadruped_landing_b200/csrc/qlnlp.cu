@@ -11,6 +11,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "layout.h"
@@ -42,8 +43,10 @@ int fail(int code, const char* fmt, ...)
 // per-stream scratch of the host-pointer pipeline
 struct HostLane {
     cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr; // the chunk's last copy has landed
     int64_t cap = 0;            // evaluations the buffers hold
     double *Z = nullptr, *x0 = nullptr, *xf = nullptr, *f = nullptr, *grad = nullptr, *g = nullptr, *jac = nullptr;
+    double* stage = nullptr;    // pinned host rows of SPARSE_TRUE values awaiting expansion (compact transfer)
 };
 
 }  // namespace
@@ -73,6 +76,7 @@ struct qlnlp_handle_s {
     bool fastdiv = false;              // reciprocal-FMA division verified exact for this model
     int64_t last_launch[5] = {0, 0, 0, 0, 0};
     HostLane lanes[2];
+    std::vector<int32_t> true2block;   // position of every SPARSE_TRUE value inside a SPARSE_BLOCK row
     int64_t ldz_e = 0, ldgrad_e = 0, ldg_e = 0, ldjac_e = 0;   // even leading dimensions of the scratch
 };
 
@@ -251,12 +255,15 @@ int ensure_device(qlnlp_handle h)
         if (nb < 1) return fail(QLNLP_ECUDA, "kernel does not fit on an SM");
         h->blocks_per_sm[wj] = nb;
     }
-    for (auto& ln : h->lanes) CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    for (auto& ln : h->lanes) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    }
     h->dev_ready = true;
     return QLNLP_OK;
 }
 
-int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t stream)
+int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t stream, int jm_force = -1)
 {
     const QlClass& c = h->cls;
     if (B < 0) return fail(QLNLP_EINVAL, "negative batch");
@@ -264,7 +271,9 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     if (io->ldz < c.n_nlp) return fail(QLNLP_EINVAL, "ldz %lld < n_nlp %d", (long long)io->ldz, c.n_nlp);
     if (io->grad && io->ldgrad < c.n_nlp) return fail(QLNLP_EINVAL, "ldgrad %lld < n_nlp %d", (long long)io->ldgrad, c.n_nlp);
     if (io->g && io->ldg < c.m_nlp) return fail(QLNLP_EINVAL, "ldg %lld < m_nlp %d", (long long)io->ldg, c.m_nlp);
-    if (io->jac && io->ldjac < batch_nnz(h)) return fail(QLNLP_EINVAL, "ldjac %lld < nnz %d", (long long)io->ldjac, batch_nnz(h));
+    const int jm_jac = jm_force >= 0 ? jm_force : batch_jm(h);
+    const int nnz_jac = jm_jac == ql::JM_TRUE ? c.nnz_true : c.nnz;
+    if (io->jac && io->ldjac < nnz_jac) return fail(QLNLP_EINVAL, "ldjac %lld < nnz %d", (long long)io->ldjac, nnz_jac);
     if ((reinterpret_cast<uintptr_t>(io->Z) & 7) != 0) return fail(QLNLP_EINVAL, "Z must be 8-byte aligned");
     if (B == 0) return QLNLP_OK;
 
@@ -288,7 +297,7 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     P.bulk = (io->jac && (reinterpret_cast<uintptr_t>(io->jac) & 15) == 0 && (io->ldjac & 1) == 0) ? 1 : 0;
     P.zbulk = ((reinterpret_cast<uintptr_t>(io->Z) & 15) == 0 && (io->ldz & 1) == 0) ? 1 : 0;   // ldz even > n_nlp (odd)
 
-    const int wj = io->jac ? batch_jm(h) : ql::JM_NONE;
+    const int wj = io->jac ? jm_jac : ql::JM_NONE;
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm[wj];
     const int grid = (int)std::min<int64_t>(B, resident);
     void* args[] = {&P};
@@ -303,6 +312,8 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
 
 void free_lane(HostLane& ln)
 {
+    if (ln.stage) cudaFreeHost(ln.stage);
+    ln.stage = nullptr;
     cudaFree(ln.Z); cudaFree(ln.x0); cudaFree(ln.xf); cudaFree(ln.f); cudaFree(ln.grad); cudaFree(ln.g); cudaFree(ln.jac);
     ln.Z = ln.x0 = ln.xf = ln.f = ln.grad = ln.g = ln.jac = nullptr;
     ln.cap = 0;
@@ -324,8 +335,59 @@ int reserve_lane(qlnlp_handle h, HostLane& ln, int64_t cap)
     CUDA_TRY(cudaMalloc(&ln.grad, sizeof(double) * cap * h->ldgrad_e));
     CUDA_TRY(cudaMalloc(&ln.g, sizeof(double) * cap * h->ldg_e));
     CUDA_TRY(cudaMalloc(&ln.jac, sizeof(double) * cap * h->ldjac_e));
+    if (batch_jm(h) == ql::JM_BLOCK)
+        CUDA_TRY(cudaHostAlloc(&ln.stage, sizeof(double) * cap * ((c.nnz_true + 1) & ~1), cudaHostAllocDefault));
     ln.cap = cap;
     return QLNLP_OK;
+}
+
+// ---- compact transfer of SPARSE_BLOCK rows to the host -----------------------------------------------------
+// 85 % of a SPARSE_BLOCK row are structural zeros.  For host-pointer batches the device therefore produces the
+// SPARSE_TRUE values (38.7 KB instead of 257 KB per evaluation cross PCIe) and host threads rebuild the rows the
+// caller asked for: zero-fill + scatter through `true2block`.  No arithmetic happens on the host.
+void build_true2block(qlnlp_handle h)
+{
+    const QlClass& c = h->cls;
+    std::vector<int64_t> rb(c.nnz), cb(c.nnz), rt(c.nnz_true), ct(c.nnz_true);
+    sparse_block_structure(c, rb.data(), cb.data());
+    sparse_true_structure(c, rt.data(), ct.data());
+    h->true2block.resize(c.nnz_true);
+    int64_t j = 0;
+    for (int64_t i = 0; i < c.nnz_true; ++i) {          // both lists are column-major sorted; TRUE is a sub-sequence
+        while (rb[j] != rt[i] || cb[j] != ct[i]) ++j;
+        h->true2block[i] = (int32_t)j;
+    }
+}
+
+int host_threads()
+{
+    if (const char* e = std::getenv("QLNLP_HOST_THREADS")) {
+        const int n = std::atoi(e);
+        if (n > 0) return n;
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(hw ? hw : 4, 64);
+}
+
+void expand_rows(const qlnlp_handle h, const double* stage, int64_t ldt, double* dst, int64_t lddst, int64_t rows)
+{
+    const int nnz_t = h->cls.nnz_true, nnz_b = h->cls.nnz;
+    const int32_t* map = h->true2block.data();
+    const int T = (int)std::min<int64_t>(host_threads(), rows);
+    auto work = [&](int t) {
+        for (int64_t r = t; r < rows; r += T) {
+            double* out = dst + r * lddst;
+            const double* in = stage + r * ldt;
+            std::memset(out, 0, sizeof(double) * (size_t)nnz_b);
+            for (int i = 0; i < nnz_t; ++i) out[map[i]] = in[i];
+        }
+    };
+    if (T <= 1) { work(0); return; }
+    std::vector<std::thread> pool;
+    pool.reserve(T - 1);
+    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
 }
 
 // rows of `width` doubles: host (ld_h) <-> device (ld_d)
@@ -337,7 +399,8 @@ cudaError_t copy_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src
     return cudaMemcpy2DAsync(dst, sizeof(double) * ld_dst, src, sizeof(double) * ld_src, sizeof(double) * width, rows, kind, s);
 }
 
-constexpr int64_t HOST_CHUNK = 512;   // evaluations per pipeline stage (~146 MB of outputs)
+constexpr int64_t HOST_CHUNK = 512;   // evaluations per pipeline stage
+constexpr int64_t COMPACT_MIN_B = 64; // below this the rows are copied as they are
 
 int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
 {
@@ -354,6 +417,18 @@ int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
         int rc = reserve_lane(h, h->lanes[l], chunk);
         if (rc) return rc;
     }
+    // SPARSE_BLOCK rows for a host caller: ship the structural non-zeros, rebuild the rows with host threads
+    const bool compact = io->jac && batch_jm(h) == ql::JM_BLOCK && B >= COMPACT_MIN_B;
+    const int64_t ldt = (c.nnz_true + 1) & ~1;
+    if (compact && h->true2block.empty()) build_true2block(h);
+
+    struct Pending { HostLane* ln; int64_t b0, nb; } prev = {nullptr, 0, 0};
+    auto finish = [&](const Pending& pd) -> int {
+        if (!pd.ln) return QLNLP_OK;
+        CUDA_TRY(cudaEventSynchronize(pd.ln->done));
+        expand_rows(h, pd.ln->stage, ldt, io->jac + pd.b0 * io->ldjac, io->ldjac, pd.nb);
+        return QLNLP_OK;
+    };
     int li = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, li ^= 1) {
         HostLane& ln = h->lanes[nlanes == 2 ? li : 0];
@@ -370,14 +445,22 @@ int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
         d.f = io->f ? ln.f : nullptr;
         d.grad = io->grad ? ln.grad : nullptr; d.ldgrad = h->ldgrad_e;
         d.g = io->g ? ln.g : nullptr; d.ldg = h->ldg_e;
-        d.jac = io->jac ? ln.jac : nullptr; d.ldjac = h->ldjac_e;
-        int rc = launch(h, nb, &d, s);
+        d.jac = io->jac ? ln.jac : nullptr; d.ldjac = compact ? ldt : h->ldjac_e;
+        int rc = launch(h, nb, &d, s, compact ? ql::JM_TRUE : -1);
         if (rc) return rc;
         if (io->f) CUDA_TRY(cudaMemcpyAsync(io->f + b0, ln.f, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
         if (io->grad) CUDA_TRY(copy_rows(io->grad + b0 * io->ldgrad, io->ldgrad, ln.grad, h->ldgrad_e, c.n_nlp, nb, cudaMemcpyDeviceToHost, s));
         if (io->g) CUDA_TRY(copy_rows(io->g + b0 * io->ldg, io->ldg, ln.g, h->ldg_e, c.m_nlp, nb, cudaMemcpyDeviceToHost, s));
-        if (io->jac) CUDA_TRY(copy_rows(io->jac + b0 * io->ldjac, io->ldjac, ln.jac, h->ldjac_e, batch_nnz(h), nb, cudaMemcpyDeviceToHost, s));
+        if (compact) {
+            CUDA_TRY(cudaMemcpyAsync(ln.stage, ln.jac, sizeof(double) * nb * ldt, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaEventRecord(ln.done, s));
+            if (int rc2 = finish(prev)) return rc2;          // expand the previous chunk while this one is in flight
+            prev = {&ln, b0, nb};
+        } else if (io->jac) {
+            CUDA_TRY(copy_rows(io->jac + b0 * io->ldjac, io->ldjac, ln.jac, h->ldjac_e, batch_nnz(h), nb, cudaMemcpyDeviceToHost, s));
+        }
     }
+    if (int rc = finish(prev)) return rc;
     for (int l = 0; l < nlanes; ++l) CUDA_TRY(cudaStreamSynchronize(h->lanes[l].stream));
     return QLNLP_OK;
 }
@@ -444,6 +527,7 @@ int qlnlp_destroy(qlnlp_handle h)
             if (ln.stream) cudaStreamSynchronize(ln.stream);
             free_lane(ln);
             if (ln.stream) cudaStreamDestroy(ln.stream);
+            if (ln.done) cudaEventDestroy(ln.done);
         }
         cudaFree(h->d_cost); cudaFree(h->d_x0xf); cudaFree(h->d_segs); cudaFree(h->d_seg_begin);
         cudaFree(h->d_dense_lin); cudaFree(h->d_dense);
