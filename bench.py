@@ -319,8 +319,11 @@ def run_gpu(args):
             "config": workload_config(n_gpus, "f, grad_f, g, SPARSE_BLOCK Jacobian values (full evaluation)"),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "path": "qlnlp_eval_batch_host: pinned host buffers, 512-evaluation chunks "
-                                                 "pipelined over 2 streams; bound by PCIe D2H of 285 KB/eval"},
+                    "steps": e2e_steps, "path": "qlnlp_eval_batch_host on pinned host buffers: 512-evaluation chunks pipelined "
+                                                 "over 2 streams; the 32,161 SPARSE_BLOCK values per evaluation cross PCIe as their "
+                                                 "4,840 structural non-zeros and are rebuilt into the caller's rows by host threads "
+                                                 "(non-temporal zero-fill + scatter, no arithmetic); bound by host memory write bandwidth",
+                    "pcie_d2h_bytes_per_step": B_PER_GPU * (1 + nlp.n_nlp + nlp.m_nlp + 4840) * 8},
             "gpu_launches": args.steps * n_gpus,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),

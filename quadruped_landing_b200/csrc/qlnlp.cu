@@ -3,6 +3,9 @@
 #include "../../include/qlnlp.h"
 
 #include <cuda_runtime.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>      // _mm_stream_pd: rebuild host rows without read-for-ownership traffic
+#endif
 
 #include <cmath>
 #include <cstdarg>
@@ -374,13 +377,33 @@ void expand_rows(const qlnlp_handle h, const double* stage, int64_t ldt, double*
     const int nnz_t = h->cls.nnz_true, nnz_b = h->cls.nnz;
     const int32_t* map = h->true2block.data();
     const int T = (int)std::min<int64_t>(host_threads(), rows);
+    // Rows are produced front to back, a 16-byte pair at a time, merging the (sorted) non-zero positions into
+    // a stream of zeros; on x86-64 the pairs go out as non-temporal stores, so the row is written once and
+    // never read (a memset + scatter would first pull every line into the cache).
     auto work = [&](int t) {
         for (int64_t r = t; r < rows; r += T) {
             double* out = dst + r * lddst;
             const double* in = stage + r * ldt;
-            std::memset(out, 0, sizeof(double) * (size_t)nnz_b);
-            for (int i = 0; i < nnz_t; ++i) out[map[i]] = in[i];
+            int i = 0, pos = 0;
+            if ((reinterpret_cast<uintptr_t>(out) & 15) != 0 && nnz_b > 0) {     // 8-byte aligned row: peel one element
+                out[0] = (i < nnz_t && map[i] == 0) ? in[i++] : 0.0;
+                pos = 1;
+            }
+            for (; pos + 1 < nnz_b; pos += 2) {
+                double a = 0.0, b = 0.0;
+                if (i < nnz_t && map[i] == pos) a = in[i++];
+                if (i < nnz_t && map[i] == pos + 1) b = in[i++];
+#if defined(__x86_64__)
+                _mm_stream_pd(out + pos, _mm_set_pd(b, a));
+#else
+                out[pos] = a; out[pos + 1] = b;
+#endif
+            }
+            if (pos < nnz_b) out[pos] = (i < nnz_t && map[i] == pos) ? in[i++] : 0.0;
         }
+#if defined(__x86_64__)
+        _mm_sfence();
+#endif
     };
     if (T <= 1) { work(0); return; }
     std::vector<std::thread> pool;
