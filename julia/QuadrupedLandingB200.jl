@@ -27,6 +27,7 @@ end
 
 const JAC_SPARSE_BLOCK = Cint(0)
 const JAC_DENSE = Cint(1)
+const JAC_SPARSE_TRUE = Cint(2)
 
 check(rc::Cint) = rc == 0 || error("qlnlp error $rc: " * unsafe_string(ccall((:qlnlp_last_error, LIBQLNLP), Cstring, ())))
 
@@ -39,14 +40,15 @@ mutable struct CudaHybridNLP <: MOI.AbstractNLPEvaluator
 end
 
 """
-    CudaHybridNLP(nlp; sparse=true, device=0)
+    CudaHybridNLP(nlp; sparse=true, pattern=:block, device=0)
 
 Build the GPU evaluator from the reference's `HybridNLP` (src/nlp.jl:13-84).  `sparse=false` reports the
 dense m_nlp x n_nlp structure exactly like src/moi.jl:31-33; `sparse=true` reports SPARSE_BLOCK, the
 column-major filter of the entries `jac_c!` assigns (32,161 instead of 1,327,995 pairs at the default
-instance -- this is what removes the 575 s Ipopt spends on the dense structure, src/main.ipynb:724).
+instance -- this is what removes the 575 s Ipopt spends on the dense structure, src/main.ipynb:724), or with
+`pattern=:true` only the 4,840 structurally non-zero entries.
 """
-function CudaHybridNLP(nlp; sparse::Bool=true, device::Integer=0)
+function CudaHybridNLP(nlp; sparse::Bool=true, pattern::Symbol=:block, device::Integer=0)
     N = nlp.N
     Q = Matrix{Cdouble}(undef, 15, N); R = Matrix{Cdouble}(undef, 5, N)
     q = Matrix{Cdouble}(undef, 15, N); r = Matrix{Cdouble}(undef, 5, N); c = Vector{Cdouble}(undef, N)
@@ -59,7 +61,8 @@ function CudaHybridNLP(nlp; sparse::Bool=true, device::Integer=0)
                              Tuple(nlp.x0), Tuple(nlp.xf), pointer(Q), pointer(R), pointer(q), pointer(r), pointer(c)))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve Q R q r c check(ccall((:qlnlp_create, LIBQLNLP), Cint,
-        (Ref{QlProblemDesc}, Cint, Cint, Ref{Ptr{Cvoid}}), desc, device, sparse ? JAC_SPARSE_BLOCK : JAC_DENSE, h))
+        (Ref{QlProblemDesc}, Cint, Cint, Ref{Ptr{Cvoid}}), desc, device,
+        sparse ? (pattern == :true ? JAC_SPARSE_TRUE : JAC_SPARSE_BLOCK) : JAC_DENSE, h))
     n = Ref{Int64}(0); mm = Ref{Int64}(0); nnz = Ref{Int64}(0); nb = Ref{Int64}(0)
     check(ccall((:qlnlp_dims, LIBQLNLP), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Int64}), h[], n, mm, nnz, nb))
     ev = CudaHybridNLP(h[], n[], mm[], nnz[], Any[Q, R, q, r, c])
