@@ -228,7 +228,12 @@ def run_gpu(args):
     prob = ql.default_problem()
     nlp = ql.HybridNLP.from_problem(prob, device=local)
     host_sets = make_inputs(prob, rank, N_INPUT_SETS)
-    Zs = [torch.from_numpy(z).to(dev) for z in host_sets]
+    # rows padded to an even length (1216 doubles): 16-byte aligned rows let the kernel fetch a vector with one TMA load
+    Zs = []
+    for z in host_sets:
+        zp = torch.zeros((B_PER_GPU, ql.even_ld(prob.n_nlp)), dtype=torch.float64, device=dev)
+        zp[:, :prob.n_nlp] = torch.from_numpy(z).to(dev)
+        Zs.append(zp[:, :prob.n_nlp])
     want = ("f", "grad", "g", "jac")
     out = nlp.eval_batch(Zs[0], want=want)
     torch.cuda.synchronize()

@@ -256,6 +256,10 @@ int ensure_device(qlnlp_handle h)
         int nb = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, h->smem[wj]));
         if (nb < 1) return fail(QLNLP_ECUDA, "kernel does not fit on an SM");
+        if (const char* e = std::getenv("QLNLP_BLOCKS_PER_SM")) {       // tuning knob: fewer resident warps per SM
+            const int cap = std::atoi(e);
+            if (cap >= 1 && cap < nb) nb = cap;
+        }
         h->blocks_per_sm[wj] = nb;
     }
     for (auto& ln : h->lanes) {

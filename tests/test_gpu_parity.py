@@ -51,7 +51,14 @@ def _bases(p, golden):
 
 
 def _dev_eval(nlp, Z, **kw):
-    Zd = torch.from_numpy(Z).cuda()
+    # alternate between tightly packed rows (odd ld: cp.async staging) and rows padded to an even length
+    # (16-byte aligned: one TMA bulk load per vector) so both input paths are exercised by every test
+    _dev_eval.flip = not getattr(_dev_eval, "flip", False)
+    if _dev_eval.flip:
+        Zd = torch.zeros((Z.shape[0], Z.shape[1] + 1), dtype=torch.float64, device="cuda")[:, :Z.shape[1]]
+        Zd.copy_(torch.from_numpy(Z))
+    else:
+        Zd = torch.from_numpy(Z).cuda()
     kw = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
     out = nlp.eval_batch(Zd, **kw)
     torch.cuda.synchronize()
@@ -131,6 +138,21 @@ def test_host_pointer_batch_and_partial_outputs(dflt, golden):
     assert_same_bits(nlp, only, {"g": ref["g"][:5]})
     only = nlp.eval_batch_host(Z[:5], want=("f", "grad"))
     assert_same_bits(nlp, only, {"grad": ref["grad"][:5], "f": ref["f"][:5]})
+
+
+def test_both_input_staging_paths_agree(dflt, golden):
+    """Z rows padded to an even length are fetched with one TMA bulk load, tightly packed rows with cp.async."""
+    p, nlp, o = dflt
+    Z = perturbed_batch(p, _bases(p, golden), 777, 1e-2, 31)
+    packed = torch.from_numpy(Z).cuda()
+    padded = torch.full((777, 1216), float("nan"), dtype=torch.float64, device="cuda")
+    padded[:, :1215] = packed
+    a = nlp.eval_batch(packed)
+    b = nlp.eval_batch(padded[:, :1215])
+    torch.cuda.synchronize()
+    for k in ("f", "grad", "g", "jac"):
+        assert torch.equal(a[k], b[k]), k
+    assert_same_bits(nlp, {k: v.cpu().numpy() for k, v in b.items()}, o.eval_batch(Z))
 
 
 def test_unaligned_jacobian_rows_take_the_plain_store_path(dflt, golden):

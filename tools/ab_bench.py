@@ -23,7 +23,8 @@ Z = ql.initial_guess(p)[None, :] + 1e-2 * rng.standard_normal((4096, p.n_nlp))
 Z[:, 19::20] = np.clip(Z[:, 19::20], 1e-3, 2e-2)
 res = {}
 for Bt in (4096, 65536):
-    Zt = torch.from_numpy(Z).cuda().repeat(Bt // 4096, 1).contiguous()
+    Zt = torch.zeros((Bt, 1216), dtype=torch.float64, device="cuda")[:, :1215]     # padded rows: TMA load path
+    Zt.copy_(torch.from_numpy(Z).cuda().repeat(Bt // 4096, 1))
     out = nlp.eval_batch(Zt)
     torch.cuda.synchronize()
     for want in (("f", "grad", "g", "jac"), ("g", "jac")):
