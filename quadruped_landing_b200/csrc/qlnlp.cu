@@ -305,14 +305,21 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     P.zbulk = ((reinterpret_cast<uintptr_t>(io->Z) & 15) == 0 && (io->ldz & 1) == 0) ? 1 : 0;   // ldz even > n_nlp (odd)
 
     const int wj = io->jac ? jm_jac : ql::JM_NONE;
-    const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm[wj];
+    // Resident warps per SM.  The SPARSE_BLOCK stream is store-bound, and the memory system takes the stream of
+    // fewer, faster warps better than that of many slow ones (profiles/r01_ablation.md, section 4): with long
+    // batches 5 warps/SM (4 when no cost/gradient is asked for) beat the 8 that fit; short batches keep all 8
+    // so that the last, partial round of evaluations stays short.
+    int per_sm = h->blocks_per_sm[wj];
+    if (wj == ql::JM_BLOCK && B >= 8 * (int64_t)h->sm_count * per_sm && !std::getenv("QLNLP_BLOCKS_PER_SM"))
+        per_sm = std::min(per_sm, (io->f || io->grad) ? 5 : 4);
+    const int64_t resident = (int64_t)h->sm_count * per_sm;
     const int grid = (int)std::min<int64_t>(B, resident);
     void* args[] = {&P};
     CUDA_TRY(cudaLaunchKernel(kernel_fn(wj, h->fastdiv), dim3(grid), dim3(QL_LANES), args, h->smem[wj], stream));
     h->last_launch[0] = grid;
     h->last_launch[1] = QL_LANES;
     h->last_launch[2] = (int64_t)h->smem[wj];
-    h->last_launch[3] = h->blocks_per_sm[wj];
+    h->last_launch[3] = per_sm;
     h->last_launch[4] = h->sm_count;
     return QLNLP_OK;
 }
