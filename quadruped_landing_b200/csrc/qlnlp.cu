@@ -547,7 +547,7 @@ int qlnlp_create(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_ha
     h->rmf = 1.0 / h->cls.mf;
     h->rIb = 1.0 / h->cls.Ib;
     h->fastdiv = fastdiv_is_exact(h->cls.mb) && fastdiv_is_exact(h->cls.mf) && fastdiv_is_exact(h->cls.Ib) &&
-                 fastdiv_is_exact(6.0);
+                 fastdiv_is_exact(6.0) && !std::getenv("QLNLP_IEEE_DIV");   // env: force the IEEE-division kernels
     *out = h;
     return QLNLP_OK;
 }

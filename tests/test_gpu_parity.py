@@ -339,3 +339,46 @@ def test_host_batch_compact_transfer_rebuilds_exact_rows(golden):
     h2 = nlp_d.eval_batch_host(Z[:200], x0=x0)
     d2 = _dev_eval(nlp, Z[:200], x0=x0)
     assert np.array_equal(h2["jac"], d2["jac"]) and np.array_equal(h2["g"], d2["g"])
+
+
+def _random_problem(seed, N=37, kt=12, im=2):
+    """A problem with nothing at its default: model constants, per-knot cost tables, boundary states."""
+    rng = np.random.default_rng(seed)
+    model = ql.PlanarQuadruped(g=-3.71 - rng.random(), mb=7.3 + rng.random(), mf=0.23 + 0.1 * rng.random(),
+                               lb=0.61 + 0.1 * rng.random(), l1=0.3, l2=0.2)
+    obj = [ql.LQRCost(rng.uniform(0, 20, 15), rng.uniform(0, 1, 5), rng.normal(size=15), rng.normal(size=5) * 30)
+           for _ in range(N)]
+    return ql.ProblemData.from_costs(model, obj, im, kt, N, rng.normal(size=15), rng.normal(size=15))
+
+
+@pytest.mark.parametrize("ieee_div", [False, True])
+def test_non_default_model_and_cost_tables(ieee_div, monkeypatch):
+    """Per-knot random Q/R/q/r/c and non-default model constants; both division instantiations of the kernel
+    (reciprocal-FMA and IEEE) must give the oracle's bits."""
+    if ieee_div:
+        monkeypatch.setenv("QLNLP_IEEE_DIV", "1")
+    p = _random_problem(17)
+    nlp, o = ql.HybridNLP.from_problem(p), Oracle(p)
+    rng = np.random.default_rng(18)
+    Z = rng.normal(size=(500, p.n_nlp))
+    Z[:, 19::20] = rng.uniform(1e-3, 2e-2, size=(500, p.N - 1))
+    got = _dev_eval(nlp, Z)
+    assert_same_bits(nlp, got, o.eval_batch(Z))
+    nlp_t = ql.HybridNLP.from_problem(p, pattern="true")
+    assert_same_bits(nlp_t, _dev_eval(nlp_t, Z[:100]), o.eval_batch(Z[:100], pattern="true"))
+
+
+def test_non_finite_inputs_do_not_crash_and_stay_local(dflt):
+    """The reference does no checks; NaN/Inf propagate.  Here they propagate through every operation that is kept;
+    structurally zero Jacobian entries stay 0 (the reference would produce NaN there: 0*NaN).  Other evaluations
+    of the batch are unaffected."""
+    p, nlp, o = dflt
+    Z = perturbed_batch(p, [ql.initial_guess(p)], 8, 1e-2, 3)
+    Z[3, 20 * 10 + 1] = np.nan          # yb of knot 11
+    Z[5, 20 * 40 + 16] = np.inf         # F1y of knot 41
+    got = _dev_eval(nlp, Z)
+    ref = o.eval_batch(Z)
+    clean = [0, 1, 2, 4, 6, 7]
+    assert_same_bits(nlp, {k: v[clean] for k, v in got.items()}, {k: v[clean] for k, v in ref.items()})
+    assert np.isnan(got["f"][3]) and np.isnan(got["g"][3]).any() and not np.isfinite(got["f"][5])
+    assert np.isfinite(got["g"][3]).sum() > 900          # only the rows that touch knot 10/11 are affected
