@@ -382,3 +382,15 @@ def test_non_finite_inputs_do_not_crash_and_stay_local(dflt):
     assert_same_bits(nlp, {k: v[clean] for k, v in got.items()}, {k: v[clean] for k, v in ref.items()})
     assert np.isnan(got["f"][3]) and np.isnan(got["g"][3]).any() and not np.isfinite(got["f"][5])
     assert np.isfinite(got["g"][3]).sum() > 900          # only the rows that touch knot 10/11 are affected
+
+
+def test_handles_of_different_sizes_coexist():
+    """Kernel attributes are per function, not per handle: a small problem created later must not shrink the
+    shared-memory limit a larger, older handle needs (regression test)."""
+    big = ql.HybridNLP.from_problem(ql.build_problem(N=121, k_trans=41))
+    zb = perturbed_batch(big.prob, [ql.initial_guess(big.prob)], 4, 1e-2, 1)
+    a = _dev_eval(big, zb)
+    small = ql.HybridNLP.from_problem(ql.build_problem(N=5, k_trans=3))
+    _dev_eval(small, perturbed_batch(small.prob, [ql.initial_guess(small.prob)], 4, 1e-2, 1))
+    b = _dev_eval(big, zb)
+    assert np.array_equal(a["jac"], b["jac"])
