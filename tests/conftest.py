@@ -8,6 +8,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # fp64 parity tolerance stated by BASELINE.json's north_star: 1e-12 relative / 1e-14 absolute
 RTOL = 1e-12

@@ -394,3 +394,20 @@ def test_handles_of_different_sizes_coexist():
     _dev_eval(small, perturbed_batch(small.prob, [ql.initial_guess(small.prob)], 4, 1e-2, 1))
     b = _dev_eval(big, zb)
     assert np.array_equal(a["jac"], b["jac"])
+
+
+def test_solver_loop_on_the_gpu_evaluator():
+    """the solve() glue of moi.jl:46-103 driving the GPU evaluator through the four MOI callbacks
+    with the SPARSE_TRUE structure (a few iterations; the callbacks must agree with the oracle at the iterate)."""
+    import warnings
+    from quadruped_landing_b200.solve import solve
+    p = ql.build_problem(N=9, k_trans=4)
+    nlp, o = ql.HybridNLP.from_problem(p, pattern="true"), Oracle(p)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = solve(ql.initial_guess(p), nlp, tol=1e-3, c_tol=1e-3, max_iter=5, backend="trust-constr")
+    assert res.iterations == 5 and min(res.evals.values()) >= 5
+    assert abs(res.objective - o.eval_f(res.x)) <= 1e-12 * max(1.0, abs(res.objective))
+    vals = np.empty(nlp.nnz)
+    nlp.eval_constraint_jacobian(vals, res.x)
+    assert_same_bits(nlp, {"jac": vals}, {"jac": o.jac_c_sparse_true(res.x)})
