@@ -118,16 +118,19 @@ QL_HD int ql_rk4_pos(const QlClass& c, int k, int i, int j) { return ql_col_star
 // offset of the body-pos d/dtheta entry (the only other value-dependent entry) inside knot k's run
 QL_HD int ql_theta_pos(const QlClass& c, int k) { return ql_col_start(c, k, 2) + ql_col_width(c, k); }
 
-// constants of knot k's run (everything jac_c! assigns that does not depend on Z), into a zeroed image
-QL_HD void ql_write_run_constants(const QlClass& c, int k, double* run)
+// Constants of knot k's run (everything jac_c! assigns that does not depend on Z), into a zeroed image.
+// Split by "slot" so that 16 lanes can write one knot's constants in parallel: slot j < 15 = the identity-block
+// entries of state column j, slot 15 = the unit entries of the extra rows.
+QL_HD void ql_write_run_constants_slot(const QlClass& c, int k, double* run, int j)
 {
     const int cw = ql_col_width(c, k);
     const int e4 = ql_e4(c, k), e6 = ql_e6(c, k);
-    for (int j = 0; j < QL_NX; ++j) {
+    if (j < QL_NX) {
         const int cs = cw * j + (j >= 2) + (j >= 3) + (j >= 5 ? e4 : 0) + (j >= 7 ? e6 : 0);
         if (k == 1) run[cs + j] = 1.0;                         // jac_init .= I(n)            constraints.jl:228
         if (k == c.N && j < QL_NX - 1) run[cs + j] = 1.0;      // jac_term .= I(n)[1:n-1,:]   constraints.jl:229
         if (k >= 2) run[cs + (k == c.N ? QL_NX - 1 : 0) + j] = -1.0;   // D[ci, xi[k+1]] .= -I(n)   :200
+        return;
     }
     run[cw * 1 + cw] = 1.0;                                    // body-pos d/dyb              constraints.jl:267
     if (e4) run[cw * 4 + 2 + cw] = 1.0;                        // contact row on y1           :237 / :254
@@ -137,6 +140,10 @@ QL_HD void ql_write_run_constants(const QlClass& c, int k, double* run)
         run[cb + 15 * 1 + 15] = 1.0;                           // after the RK4 rows of control column 16 (F1y)
         run[cb + 15 * 3 + 1 + 15] = 1.0;                       // ... and of control column 18 (F2y)
     }
+}
+QL_HD void ql_write_run_constants(const QlClass& c, int k, double* run)
+{
+    for (int j = 0; j <= QL_NX; ++j) ql_write_run_constants_slot(c, k, run, j);
 }
 
 // ---- SPARSE_TRUE: only structurally non-zero entries (identity blocks as diagonals, RK4 blocks as their

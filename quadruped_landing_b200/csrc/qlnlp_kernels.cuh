@@ -161,13 +161,17 @@ struct Launch {
 // shared memory carve-up: staged Z (same layout as in HBM) | mbarrier | two J staging buffers | segment plan
 __host__ __device__ inline int zbuf_len(int N) { return QL_NZK * N + 2; }     // n_nlp + 1 rounded up to even, + mbarrier
 enum { JM_NONE = 0, JM_BLOCK = 1, JM_TRUE = 2 };     // which Jacobian value stream the kernel produces
-__host__ __device__ inline size_t smem_bytes(int N, int jm)
+__host__ __device__ inline size_t smem_jregion_bytes(int N, int jm)
 {
     const int nseg_max = (N + 1) / 2 + (N + QL_LANES - 1) / QL_LANES;
-    size_t b = sizeof(double) * (size_t)zbuf_len(N);
-    if (jm == JM_BLOCK) b += sizeof(double) * 2 * QL_JBUF + sizeof(QlSeg) * nseg_max;
-    if (jm == JM_TRUE) b += sizeof(double) * QL_TRUE_PBUF;
-    return b;
+    if (jm == JM_BLOCK) return sizeof(double) * 2 * QL_JBUF + sizeof(QlSeg) * nseg_max;
+    if (jm == JM_TRUE) return sizeof(double) * QL_TRUE_PBUF;
+    return 0;
+}
+__host__ __device__ inline size_t smem_bytes(int N, int jm, bool cost_smem)
+{
+    const int npad = (N + 31) & ~31;      // the table keeps its global layout [41][npad]; + 16 B for its mbarrier
+    return sizeof(double) * (size_t)zbuf_len(N) + smem_jregion_bytes(N, jm) + (cost_smem ? sizeof(double) * (QL_NCOST * npad + 2) : 0);
 }
 
 // Start fetching a decision vector into shared memory.  zbulk: one TMA bulk load of n+1 doubles (n is odd, the
@@ -185,7 +189,7 @@ __device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigne
     }
 }
 
-template <int JM, bool FASTDIV>
+template <int JM, bool FASTDIV, bool COST_SMEM>
 __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant__ Launch P)
 {
     constexpr bool WITH_JAC = JM != JM_NONE;
@@ -200,6 +204,17 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
     const unsigned zaddr = smem_addr(zbuf);
     const unsigned jaddr = smem_addr(jb);
     int tmpl0 = -1, tmpl1 = -1;        // template currently held by staging buffer 0 / 1
+    // cost coefficients: from shared memory ([41][N], copied once per CTA) when the launch has room for it, else
+    // from the field-major global table (L2)
+    // COST_SMEM: the whole cost table ([41][npad] doubles, ~21 KB) is fetched once per CTA with one TMA bulk load
+    double* const cost_s = reinterpret_cast<double*>(reinterpret_cast<char*>(jb) + smem_jregion_bytes(c.N, JM));
+    const unsigned cbar = smem_addr(cost_s + QL_NCOST * P.npad);
+    if (COST_SMEM) {
+        if (lane == 0) mbar_init(cbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bulk_load(smem_addr(cost_s), P.cost, 8u * (unsigned)(QL_NCOST * P.npad), cbar);
+    }
 
     Consts<FASTDIV> K;
     K.g = c.g; K.mb = c.mb; K.mf = c.mf; K.Ib = c.Ib; K.rmb = P.rmb; K.rmf = P.rmf; K.rIb = P.rIb;
@@ -214,6 +229,7 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
     }
     long long b = blockIdx.x;
     if (b < P.B) stage_z(P.Z + b * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
+    if (COST_SMEM) mbar_wait(cbar, 0);      // the table lands while the first decision vector is in flight
     if (JM == JM_BLOCK) {
         // the segment plan lives in shared memory: one 16-byte record per segment
         const int4* src = reinterpret_cast<const int4*>(P.segs);
@@ -248,11 +264,18 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
 
             // ---- 2. cost and gradient (costs.jl:6-34, quadratic_cost.jl:44-52); gradient in place over Z
             if (act && (P.f || gradrow)) {
-                const double* ct = P.cost + (k - 1);
-                const int np = P.npad;
                 double cq[QL_NCOST];                // all loads first: their latency overlaps
+                if (COST_SMEM) {
+                    const double* ct = cost_s + (k - 1);
+                    const int np = P.npad;
 #pragma unroll
-                for (int i = 0; i < QL_NCOST; ++i) cq[i] = __ldg(ct + i * np);
+                    for (int i = 0; i < QL_NCOST; ++i) cq[i] = ct[i * np];
+                } else {
+                    const double* ct = P.cost + (k - 1);
+                    const int np = P.npad;
+#pragma unroll
+                    for (int i = 0; i < QL_NCOST; ++i) cq[i] = __ldg(ct + i * np);
+                }
                 const double hk = uk[4];
                 double hq = __dmul_rn(__dmul_rn(0.5, __dmul_rn(xk[0], cq[0])), xk[0]);     // 0.5*x'Q*x, folded left
                 double dq = __dmul_rn(cq[15], xk[0]);                                       // q'x
@@ -417,13 +440,15 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
                     if ((bi ? tmpl1 : tmpl0) != tm) {            // different constant image: rebuild
                         for (int i = lane; i < QL_JBUF / 2; i += QL_LANES) st_shared_zero16(baddr + 16u * i);
                         __syncwarp();
-                        if (mine) {
-                            ql_write_run_constants(c, k, buf + (roff - base));
-                            if (has_u) {
-                                if (k >= c.k_trans) ql_const_mode3(pg, jump);
-                                else if (c.init_mode == 1) ql_const_mode1(pg, jump);
-                                else ql_const_mode2(pg, jump);
-                            }
+                        {   // lanes 0-15 write the constants of knot k0, lanes 16-31 those of knot k0+1, one slot each
+                            const int kk = k0 + (lane >> 4);
+                            if ((lane >> 4) < nk)
+                                ql_write_run_constants_slot(c, kk, buf + (ql_run_off(c, kk) - base), lane & 15);
+                        }
+                        if (mine && has_u) {     // constant entries of the RK4 block, by the knot's owner lane
+                            if (k >= c.k_trans) ql_const_mode3(pg, jump);
+                            else if (c.init_mode == 1) ql_const_mode1(pg, jump);
+                            else ql_const_mode2(pg, jump);
                         }
                         if (bi) tmpl1 = tm; else tmpl0 = tm;
                     }
