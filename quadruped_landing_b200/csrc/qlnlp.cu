@@ -73,13 +73,13 @@ struct qlnlp_handle_s {
     long long* d_dense_lin = nullptr;  // DENSE mode: linear index of every SPARSE_BLOCK value
     double* d_dense = nullptr;         // DENSE mode: m x n grid
     int sm_count = 0;
-    // launch configurations [JM_NONE, JM_BLOCK, JM_TRUE] x [cost table in L2, cost table in shared memory]
-    int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    size_t smem[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    int blocks_per_sm[3] = {0, 0, 0};  // [JM_NONE, JM_BLOCK, JM_TRUE]
+    size_t smem[3] = {0, 0, 0};
     double rmb = 0, rmf = 0, rIb = 0;  // reciprocals of the divisors
     bool fastdiv = false;              // reciprocal-FMA division verified exact for this model
     int64_t last_launch[5] = {0, 0, 0, 0, 0};
     HostLane lanes[2];
+    std::map<cudaStream_t, unsigned*> tickets;   // work counters, one pair per stream the handle has launched on
     std::vector<int32_t> true2block;   // position of every SPARSE_TRUE value inside a SPARSE_BLOCK row
     int64_t ldz_e = 0, ldgrad_e = 0, ldg_e = 0, ldjac_e = 0;   // even leading dimensions of the scratch
 };
@@ -168,18 +168,11 @@ bool fastdiv_is_exact(double b)
     return true;
 }
 
-// COST_SMEM instantiations keep the cost table in shared memory (more shared memory per warp, fewer warps per SM)
-template <int JM>
-const void* kernel_fn_jm(bool fast, bool cs)
+const void* kernel_fn(int jm, bool fast)
 {
-    if (fast) return cs ? (const void*)ql::eval_kernel<JM, true, true> : (const void*)ql::eval_kernel<JM, true, false>;
-    return cs ? (const void*)ql::eval_kernel<JM, false, true> : (const void*)ql::eval_kernel<JM, false, false>;
-}
-const void* kernel_fn(int jm, bool fast, bool cs)
-{
-    if (jm == ql::JM_BLOCK) return kernel_fn_jm<ql::JM_BLOCK>(fast, cs);
-    if (jm == ql::JM_TRUE) return kernel_fn_jm<ql::JM_TRUE>(fast, cs);
-    return kernel_fn_jm<ql::JM_NONE>(fast, cs);
+    if (jm == ql::JM_BLOCK) return fast ? (const void*)ql::eval_kernel<ql::JM_BLOCK, true> : (const void*)ql::eval_kernel<ql::JM_BLOCK, false>;
+    if (jm == ql::JM_TRUE) return fast ? (const void*)ql::eval_kernel<ql::JM_TRUE, true> : (const void*)ql::eval_kernel<ql::JM_TRUE, false>;
+    return fast ? (const void*)ql::eval_kernel<ql::JM_NONE, true> : (const void*)ql::eval_kernel<ql::JM_NONE, false>;
 }
 
 // the sparse pattern batched evaluations of this handle produce (DENSE handles batch in SPARSE_BLOCK)
@@ -253,28 +246,25 @@ int ensure_device(qlnlp_handle h)
     CUDA_TRY(cudaMalloc(&h->d_seg_begin, h->seg_begin.size() * sizeof(int)));
     CUDA_TRY(cudaMemcpy(h->d_seg_begin, h->seg_begin.data(), h->seg_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
 
-    for (int wj = 0; wj < 3; ++wj)
-      for (int cs = 0; cs < 2; ++cs) {
-        h->smem[wj][cs] = ql::smem_bytes(h->cls.N, wj, cs != 0);
-        if (h->smem[wj][cs] > (size_t)prop.sharedMemPerBlockOptin) {
-            if (cs) { h->blocks_per_sm[wj][cs] = 0; continue; }       // the fat configuration is optional
-            return fail(QLNLP_EINVAL, "N=%d needs %zu B of shared memory per warp (> %zu)", h->cls.N, h->smem[wj][cs],
+    for (int wj = 0; wj < 3; ++wj) {
+        h->smem[wj] = ql::smem_bytes(h->cls.N, wj);
+        if (h->smem[wj] > (size_t)prop.sharedMemPerBlockOptin)
+            return fail(QLNLP_EINVAL, "N=%d needs %zu B of shared memory per warp (> %zu)", h->cls.N, h->smem[wj],
                         (size_t)prop.sharedMemPerBlockOptin);
-        }
-        const void* fn = kernel_fn(wj, h->fastdiv, cs != 0);
+        const void* fn = kernel_fn(wj, h->fastdiv);
         // the attribute is per FUNCTION, shared by every handle of the process: always raise it to the device
         // limit, never to this handle's own (possibly smaller) requirement
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, h->smem[wj][cs]));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, h->smem[wj]));
         if (nb < 1) return fail(QLNLP_ECUDA, "kernel does not fit on an SM");
         if (const char* e = std::getenv("QLNLP_BLOCKS_PER_SM")) {       // tuning knob: fewer resident warps per SM
             const int cap = std::atoi(e);
             if (cap >= 1 && cap < nb) nb = cap;
         }
-        h->blocks_per_sm[wj][cs] = nb;
-      }
+        h->blocks_per_sm[wj] = nb;
+    }
     for (auto& ln : h->lanes) {
         CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
@@ -318,33 +308,32 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     P.zbulk = ((reinterpret_cast<uintptr_t>(io->Z) & 15) == 0 && (io->ldz & 1) == 0) ? 1 : 0;   // ldz even > n_nlp (odd)
 
     const int wj = io->jac ? jm_jac : ql::JM_NONE;
-    // Launch configuration.  The SPARSE_BLOCK stream is store-bound, and the memory system takes the stream of
-    // few fast warps better than that of many slow ones (profiles/r01_ablation.md, sections 4-5): 4 resident warps
-    // per SM beat the 8 that fit.  With only 4 warps there is shared memory to spare, so when a cost/gradient is
-    // asked for the "fat" instantiation keeps the whole cost table in shared memory (one TMA load per CTA), which
-    // takes the L2 round trips out of every warp's critical path.
-    const bool want_cost = io->f || io->grad;
-    int cs = 0;
-    int per_sm = h->blocks_per_sm[wj][0];
-    if (wj == ql::JM_BLOCK) {
-        if (want_cost && h->blocks_per_sm[wj][1] >= 1) {
-            cs = 1;
-            per_sm = std::min(h->blocks_per_sm[wj][1], 4);
-        } else {
-            per_sm = std::min(per_sm, want_cost ? 5 : 4);
-        }
-    }
-    if (const char* e = std::getenv("QLNLP_COST_SMEM")) {              // tuning knobs (A/B runs)
-        cs = (std::atoi(e) != 0 && h->blocks_per_sm[wj][1] >= 1) ? 1 : 0;
-        per_sm = h->blocks_per_sm[wj][cs];
+    // Resident warps per SM.  The SPARSE_BLOCK stream is store-bound and the memory system takes the output of a
+    // few fast warps better than that of all 8 that fit (occupancy sweeps in profiles/r01_ablation.md, section 7):
+    // 5 per SM, 6 for short batches that also want the cost/gradient.
+    int per_sm = h->blocks_per_sm[wj];
+    if (wj == ql::JM_BLOCK && !std::getenv("QLNLP_BLOCKS_PER_SM")) {
+        const bool want_cost = io->f || io->grad;
+        const bool short_batch = B < 8 * (int64_t)h->sm_count * 6;
+        per_sm = std::min(per_sm, (want_cost && short_batch) ? 6 : 5);
     }
     const int64_t resident = (int64_t)h->sm_count * per_sm;
     const int grid = (int)std::min<int64_t>(B, resident);
+    // work counter of this stream (launches on one stream are ordered, so they can share it; the kernel's last CTA
+    // re-arms it).  Concurrent launches of the handle on different streams get different counters.
+    auto it = h->tickets.find(stream);
+    if (it == h->tickets.end()) {
+        unsigned* d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, 128));
+        CUDA_TRY(cudaMemset(d, 0, 128));
+        it = h->tickets.emplace(stream, d).first;
+    }
+    P.ticket = it->second;
     void* args[] = {&P};
-    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj, h->fastdiv, cs != 0), dim3(grid), dim3(QL_LANES), args, h->smem[wj][cs], stream));
+    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj, h->fastdiv), dim3(grid), dim3(QL_LANES), args, h->smem[wj], stream));
     h->last_launch[0] = grid;
     h->last_launch[1] = QL_LANES;
-    h->last_launch[2] = (int64_t)h->smem[wj][cs];
+    h->last_launch[2] = (int64_t)h->smem[wj];
     h->last_launch[3] = per_sm;
     h->last_launch[4] = h->sm_count;
     return QLNLP_OK;
@@ -589,6 +578,7 @@ int qlnlp_destroy(qlnlp_handle h)
             if (ln.stream) cudaStreamDestroy(ln.stream);
             if (ln.done) cudaEventDestroy(ln.done);
         }
+        for (auto& kv : h->tickets) cudaFree(kv.second);
         cudaFree(h->d_cost); cudaFree(h->d_x0xf); cudaFree(h->d_segs); cudaFree(h->d_seg_begin);
         cudaFree(h->d_dense_lin); cudaFree(h->d_dense);
     }

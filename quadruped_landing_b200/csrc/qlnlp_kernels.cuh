@@ -154,6 +154,7 @@ struct Launch {
     double* g; long long ldg;
     double* jac; long long ldjac;
     long long B;
+    unsigned* ticket;          // [0] next evaluation to hand out, [1] CTAs that have finished (both 0 between launches)
     int bulk;                  // 1: jac rows are 16 B aligned -> TMA bulk stores
     int zbulk;                 // 1: Z rows are 16 B aligned and ldz > n_nlp -> one TMA bulk load per vector
 };
@@ -168,10 +169,9 @@ __host__ __device__ inline size_t smem_jregion_bytes(int N, int jm)
     if (jm == JM_TRUE) return sizeof(double) * QL_TRUE_PBUF;
     return 0;
 }
-__host__ __device__ inline size_t smem_bytes(int N, int jm, bool cost_smem)
+__host__ __device__ inline size_t smem_bytes(int N, int jm)
 {
-    const int npad = (N + 31) & ~31;      // the table keeps its global layout [41][npad]; + 16 B for its mbarrier
-    return sizeof(double) * (size_t)zbuf_len(N) + smem_jregion_bytes(N, jm) + (cost_smem ? sizeof(double) * (QL_NCOST * npad + 2) : 0);
+    return sizeof(double) * (size_t)zbuf_len(N) + smem_jregion_bytes(N, jm);
 }
 
 // Start fetching a decision vector into shared memory.  zbulk: one TMA bulk load of n+1 doubles (n is odd, the
@@ -189,7 +189,7 @@ __device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigne
     }
 }
 
-template <int JM, bool FASTDIV, bool COST_SMEM>
+template <int JM, bool FASTDIV>
 __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant__ Launch P)
 {
     constexpr bool WITH_JAC = JM != JM_NONE;
@@ -206,16 +206,6 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
     int tmpl0 = -1, tmpl1 = -1;        // template currently held by staging buffer 0 / 1
     // cost coefficients: from shared memory ([41][N], copied once per CTA) when the launch has room for it, else
     // from the field-major global table (L2)
-    // COST_SMEM: the whole cost table ([41][npad] doubles, ~21 KB) is fetched once per CTA with one TMA bulk load
-    double* const cost_s = reinterpret_cast<double*>(reinterpret_cast<char*>(jb) + smem_jregion_bytes(c.N, JM));
-    const unsigned cbar = smem_addr(cost_s + QL_NCOST * P.npad);
-    if (COST_SMEM) {
-        if (lane == 0) mbar_init(cbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) bulk_load(smem_addr(cost_s), P.cost, 8u * (unsigned)(QL_NCOST * P.npad), cbar);
-    }
-
     Consts<FASTDIV> K;
     K.g = c.g; K.mb = c.mb; K.mf = c.mf; K.Ib = c.Ib; K.rmb = P.rmb; K.rmf = P.rmf; K.rIb = P.rIb;
     const bool first_is_y1 = (c.init_mode == 1);    // contact-first reads y1 (mode 1) or y2 (mode 2)
@@ -227,9 +217,18 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
     }
-    long long b = blockIdx.x;
+    // Work distribution: evaluations are handed out through a global ticket counter, in index order, to whichever
+    // warp is free.  Besides balancing the load this keeps the rows being written at any moment within a narrow,
+    // advancing address window, which the memory system likes much better than the drifting round-robin pattern of a
+    // static assignment (+5 % full / +10 % g+J throughput at B=65,536, profiles/r01_ablation.md section 7).
+    auto take = [&]() -> long long {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(P.ticket, 1u);
+        return (long long)__shfl_sync(0xffffffffu, t, 0);
+    };
+    long long b = take();
+    long long nb = P.B;
     if (b < P.B) stage_z(P.Z + b * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
-    if (COST_SMEM) mbar_wait(cbar, 0);      // the table lands while the first decision vector is in flight
     if (JM == JM_BLOCK) {
         // the segment plan lives in shared memory: one 16-byte record per segment
         const int4* src = reinterpret_cast<const int4*>(P.segs);
@@ -237,7 +236,7 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
         for (int i = lane; i < P.nseg; i += QL_LANES) dst[i] = __ldg(src + i);
     }
 
-    for (; b < P.B; b += gridDim.x) {
+    for (; b < P.B; b = nb) {
         if (zbulk) { mbar_wait(mbar, zphase); zphase ^= 1u; }
         else cp_async_wait_all();
         __syncwarp();
@@ -264,18 +263,11 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
 
             // ---- 2. cost and gradient (costs.jl:6-34, quadratic_cost.jl:44-52); gradient in place over Z
             if (act && (P.f || gradrow)) {
+                const double* ct = P.cost + (k - 1);
+                const int np = P.npad;
                 double cq[QL_NCOST];                // all loads first: their latency overlaps
-                if (COST_SMEM) {
-                    const double* ct = cost_s + (k - 1);
-                    const int np = P.npad;
 #pragma unroll
-                    for (int i = 0; i < QL_NCOST; ++i) cq[i] = ct[i * np];
-                } else {
-                    const double* ct = P.cost + (k - 1);
-                    const int np = P.npad;
-#pragma unroll
-                    for (int i = 0; i < QL_NCOST; ++i) cq[i] = __ldg(ct + i * np);
-                }
+                for (int i = 0; i < QL_NCOST; ++i) cq[i] = __ldg(ct + i * np);
                 const double hk = uk[4];
                 double hq = __dmul_rn(__dmul_rn(0.5, __dmul_rn(xk[0], cq[0])), xk[0]);     // 0.5*x'Q*x, folded left
                 double dq = __dmul_rn(cq[15], xk[0]);                                       // q'x
@@ -377,7 +369,7 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
             }
             if (p == c.npass - 1) {
                 // zbuf is dead: prefetch the next decision vector while the Jacobian values stream out
-                const long long nb = b + gridDim.x;
+                nb = take();
                 if (nb < P.B) stage_z(P.Z + nb * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
             }
 
@@ -486,6 +478,14 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
         }
     }
     if (WITH_JAC && P.bulk && lane == 0) bulk_wait_all();
+    // the last CTA to leave re-arms the counters for the next launch on this stream
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(P.ticket + 1, 1u) == gridDim.x - 1) {
+            P.ticket[0] = 0u;
+            P.ticket[1] = 0u;
+        }
+    }
 }
 
 // DENSE mode (single evaluations): scatter SPARSE_BLOCK values into the zeroed m x n grid
