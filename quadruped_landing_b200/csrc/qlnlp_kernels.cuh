@@ -1,7 +1,8 @@
 // qlnlp_kernels.cuh -- fused batched evaluator kernel for sm_100a (B200).
 //
 // One warp per trajectory (decision vector), one lane per knot, ceil(N/32) passes; one warp per
-// CTA so warps never synchronise with each other.  Per evaluation the warp
+// CTA so warps never synchronise with each other.  Evaluations are handed out in index order through a
+// global ticket counter (keeps the rows written at any moment in a narrow address window).  Per evaluation the warp
 //   1. stages Z through shared memory with ONE TMA bulk load per decision vector
 //      (cp.async.bulk.shared.global + mbarrier; plain cp.async when Z is not 16-byte aligned); the next
 //      vector is prefetched while the last pass streams its Jacobian values,
