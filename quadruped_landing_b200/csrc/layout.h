@@ -154,7 +154,7 @@ QL_HD void ql_write_run_constants(const QlClass& c, int k, double* run)
 #define QL_TRUE_LEN_JUMPK 71
 #define QL_TRUE_LEN_M3 72
 #define QL_TRUE_LEN_LAST 29      // knot N: 14 term-diagonal + 15 (-I)-diagonal entries
-#define QL_TRUE_PBUF 2948        // doubles of the per-pass staging buffer: 32 x (86 + 6) + parity, rounded to 16 B
+#define QL_TRUE_PBUF 1476        // doubles of the half-pass staging buffer: 16 x (86 + 6) + parity, rounded to 16 B
 
 QL_HD int ql_true_base_len(const QlClass& c, int k)
 {

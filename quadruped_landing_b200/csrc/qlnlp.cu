@@ -269,6 +269,9 @@ int ensure_device(qlnlp_handle h)
         CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
     }
+    // the set-up copies above ran on the legacy default stream and may still be in flight when cudaMemcpy returns
+    // (pageable source); launches go to arbitrary, possibly non-blocking streams, so finish the set-up first
+    CUDA_TRY(cudaDeviceSynchronize());
     h->dev_ready = true;
     return QLNLP_OK;
 }
@@ -325,7 +328,9 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     if (it == h->tickets.end()) {
         unsigned* d = nullptr;
         CUDA_TRY(cudaMalloc(&d, 128));
-        CUDA_TRY(cudaMemset(d, 0, 128));
+        // zero it ON THIS STREAM: cudaMemset on device memory is asynchronous (legacy default stream) and would
+        // not be ordered before a launch on a non-blocking stream
+        CUDA_TRY(cudaMemsetAsync(d, 0, 128, stream));
         it = h->tickets.emplace(stream, d).first;
     }
     P.ticket = it->second;
@@ -708,6 +713,7 @@ int qlnlp_eval_constraint_jacobian(qlnlp_handle h, const double* x, double* vals
         CUDA_TRY(cudaMalloc(&h->d_dense_lin, sizeof(long long) * c.nnz));
         CUDA_TRY(cudaMemcpy(h->d_dense_lin, lin.data(), sizeof(long long) * c.nnz, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMalloc(&h->d_dense, sizeof(double) * dense_n));
+        CUDA_TRY(cudaDeviceSynchronize());     // set-up copy on the default stream before work on the lane's stream
     }
     HostLane& ln = h->lanes[0];
     if (int rc = reserve_lane(h, ln, 1)) return rc;

@@ -34,6 +34,11 @@
 
 #include "layout.h"
 
+#ifndef QL_NONE_WARPS
+#define QL_NONE_WARPS 16     // resident-warp target (register cap: 128) of the instantiation without a Jacobian:
+                             // 16 warps/SM give +23..28 % over 8 (f+grad+g / g only), 20+ spill and lose
+#endif
+
 namespace ql {
 
 // ---------------------------------------------------------------- PTX helpers
@@ -191,7 +196,7 @@ __device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigne
 }
 
 template <int JM, bool FASTDIV>
-__global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant__ Launch P)
+__global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) eval_kernel(const __grid_constant__ Launch P)
 {
     constexpr bool WITH_JAC = JM != JM_NONE;
     extern __shared__ __align__(16) double smem[];
@@ -374,30 +379,36 @@ __global__ void __launch_bounds__(QL_LANES, 8) eval_kernel(const __grid_constant
                 if (nb < P.B) stage_z(P.Z + nb * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
             }
 
-            // ---- 5'. SPARSE_TRUE: every lane writes its whole run, the pass leaves as one bulk store
+            // ---- 5'. SPARSE_TRUE: every lane writes its whole run; the pass leaves as two bulk stores of 16 knots
+            // (a half-pass staging buffer keeps the shared memory per warp small enough for 8 warps per SM)
             if (JM == JM_TRUE) {
                 double* const jrow = P.jac + b * P.ldjac;
-                const int k_first = p * QL_LANES + 1, k_end = min(c.N, k_first + QL_LANES - 1) + 1;
-                const int start = ql_true_run_off(c, k_first);
-                const int end = (k_end > c.N) ? c.nnz_true : ql_true_run_off(c, k_end);
-                const int base = start & ~1;
-                if (P.bulk && lane == 0) bulk_wait_read<0>();       // the previous pass's store has read the buffer
-                __syncwarp();
-                if (act) ql_true_write_run(c, k, jv, jtheta, jaddr + 8u * (unsigned)(ql_true_run_off(c, k) - base));
-                if (P.bulk) {
-                    fence_proxy_async();
+                for (int half = 0; half < 2; ++half) {
+                    const int k_first = p * QL_LANES + 16 * half + 1;
+                    if (k_first > c.N) break;
+                    const int k_end = min(c.N, k_first + 15) + 1;
+                    const int start = ql_true_run_off(c, k_first);
+                    const int end = (k_end > c.N) ? c.nnz_true : ql_true_run_off(c, k_end);
+                    const int base = start & ~1;
+                    if (P.bulk && lane == 0) bulk_wait_read<0>();       // the previous store has read the buffer
                     __syncwarp();
-                    const int a = (start + 1) & ~1, e = end & ~1;
-                    if (lane == 0) {
-                        if (e > a) bulk_store(jrow + a, jaddr + 8u * (unsigned)(a - base), 8u * (unsigned)(e - a));
-                        bulk_commit();
+                    if (act && (lane >> 4) == half)
+                        ql_true_write_run(c, k, jv, jtheta, jaddr + 8u * (unsigned)(ql_true_run_off(c, k) - base));
+                    if (P.bulk) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        const int a = (start + 1) & ~1, e = end & ~1;
+                        if (lane == 0) {
+                            if (e > a) bulk_store(jrow + a, jaddr + 8u * (unsigned)(a - base), 8u * (unsigned)(e - a));
+                            bulk_commit();
+                        }
+                        if (lane == 1 && (start & 1)) jrow[start] = jb[start - base];
+                        if (lane == 2 && (end & 1)) jrow[end - 1] = jb[end - 1 - base];
+                    } else {
+                        __syncwarp();
+                        for (int i = lane; i < end - start; i += QL_LANES) jrow[start + i] = jb[start - base + i];
+                        __syncwarp();
                     }
-                    if (lane == 1 && (start & 1)) jrow[start] = jb[start - base];
-                    if (lane == 2 && (end & 1)) jrow[end - 1] = jb[end - 1 - base];
-                } else {
-                    __syncwarp();
-                    for (int i = lane; i < end - start; i += QL_LANES) jrow[start + i] = jb[start - base + i];
-                    __syncwarp();
                 }
             }
 
