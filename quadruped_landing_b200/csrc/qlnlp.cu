@@ -577,6 +577,7 @@ int qlnlp_destroy(qlnlp_handle h)
     if (!h) return QLNLP_OK;
     if (h->dev_ready) {
         cudaSetDevice(h->device);
+        cudaDeviceSynchronize();     // launches on caller streams may still use the handle's tables and counters
         for (auto& ln : h->lanes) {
             if (ln.stream) cudaStreamSynchronize(ln.stream);
             free_lane(ln);
