@@ -38,18 +38,29 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/qlnlp.cu -> libqlnlp.so if sources are newer than the library."""
+    """Compile csrc/qlnlp.cu -> libqlnlp.so if sources are newer than the library.
+
+    Safe under concurrent callers (e.g. the ranks of a torchrun job): the build is serialised with a file lock
+    and the library is replaced atomically."""
+    import fcntl
+
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stdout + res.stderr)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():          # another process built it while we waited
+            return LIB
+        tmp = f"{LIB}.tmp.{os.getpid()}"
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        os.replace(tmp, LIB)
+        if verbose:
+            print(res.stdout + res.stderr)
     return LIB
 
 
