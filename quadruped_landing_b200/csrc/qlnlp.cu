@@ -399,8 +399,14 @@ int host_threads()
         const int n = std::atoi(e);
         if (n > 0) return n;
     }
-    const unsigned hw = std::thread::hardware_concurrency();
-    return (int)std::min<unsigned>(hw ? hw : 4, 64);
+    unsigned hw = std::thread::hardware_concurrency();
+    if (!hw) hw = 4;
+    // one process per GPU (torchrun): share the host cores between the ranks of this node
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) {
+        const int n = std::atoi(e);
+        if (n > 1) hw = std::max(1u, hw / (unsigned)n);
+    }
+    return (int)std::min<unsigned>(hw, 64);
 }
 
 void expand_rows(const qlnlp_handle h, const double* stage, int64_t ldt, double* dst, int64_t lddst, int64_t rows)
