@@ -80,3 +80,32 @@ def test_evaluation_fails_loudly_without_a_gpu():
     assert e.value.code == ev.QLNLP_ENODEVICE and "no CPU path" in str(e.value)
     with pytest.raises(ql.QlnlpError):
         nlp.eval_batch_host(np.zeros((2, 1215)))
+
+
+def _build_demo(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "qlnlp_demo")
+    ql.load_library()                                      # makes sure libqlnlp.so exists
+    subprocess.run(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "qlnlp_demo.c"),
+                    "-L" + os.path.join(ROOT, "quadruped_landing_b200"), "-lqlnlp", "-lm", "-o", exe], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "quadruped_landing_b200"))
+    return subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_plain_c_program_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/qlnlp_demo.c uses nothing but include/qlnlp.h (Ipopt-shaped C callbacks): it must link against the
+    shared library, answer the host-only queries and report the missing device instead of computing on the CPU."""
+    r = _build_demo(tmp_path)
+    assert "variables 1215  constraints 1093  jacobian nonzeros 32161" in r.stdout
+    assert r.returncode == 2 and "no CPU path" in r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_program_reproduces_iteration_zero(tmp_path):
+    """Same program on a B200: the objective at Z0 and the primal infeasibility Ipopt prints at iteration 0
+    (src/main.ipynb:232: inf_pr 3.13e-01)."""
+    r = _build_demo(tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "objective(Z0) = 1.5438467869136" in r.stdout and "inf_pr(Z0) = 3.13" in r.stdout
+    assert "first structure entries: (1,1) (2,1) ... last (929,1215); J[0] = 1" in r.stdout
