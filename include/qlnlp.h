@@ -128,6 +128,23 @@ typedef struct {
  * synchronising.  One fused kernel evaluates everything requested. */
 int qlnlp_eval_batch_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, void* stream);
 
+/* Ragged batches: problems of different size (several handles = several (N, k_trans, init_mode) classes) packed
+ * back to back in flat arrays.  One call evaluates the B problems of THIS handle's class; the b-th of them is problem
+ * number i = index[b] (or b when index is NULL) of the flat batch and its rows start at
+ *   io->Z + z_off[i],  io->grad + z_off[i],  io->g + g_off[i],  io->jac + jac_off[i]     (offsets in doubles)
+ * while io->f, io->x0, io->xf are indexed by i.  The ld fields of io are ignored.  All pointers are device pointers.
+ * Rows whose jac address is 16-byte aligned take the TMA store path, the others the plain one. */
+typedef struct {
+    const int64_t* index;    /* [B] or NULL */
+    const int64_t* z_off;    /* [number of problems] */
+    const int64_t* g_off;    /* required when io->g is set */
+    const int64_t* jac_off;  /* required when io->jac is set */
+    int64_t flags;           /* QLNLP_RAGGED_Z_PADDED: every z_off is even and every Z row is followed by at least one
+                                readable double (rows padded to an even length): Z is then fetched with TMA loads */
+} qlnlp_ragged_io;
+#define QLNLP_RAGGED_Z_PADDED 1
+int qlnlp_eval_ragged_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, const qlnlp_ragged_io* rg, void* stream);
+
 /* All pointers are HOST pointers.  Copies Z (and x0/xf) to the device, evaluates, copies the
  * requested outputs back, and returns when they are in place.  Work is pipelined in chunks over
  * two streams so copies overlap the kernel. */

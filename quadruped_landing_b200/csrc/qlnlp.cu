@@ -168,11 +168,18 @@ bool fastdiv_is_exact(double b)
     return true;
 }
 
-const void* kernel_fn(int jm, bool fast)
+template <int JM>
+const void* kernel_fn_jm(bool fast, bool ragged)
 {
-    if (jm == ql::JM_BLOCK) return fast ? (const void*)ql::eval_kernel<ql::JM_BLOCK, true> : (const void*)ql::eval_kernel<ql::JM_BLOCK, false>;
-    if (jm == ql::JM_TRUE) return fast ? (const void*)ql::eval_kernel<ql::JM_TRUE, true> : (const void*)ql::eval_kernel<ql::JM_TRUE, false>;
-    return fast ? (const void*)ql::eval_kernel<ql::JM_NONE, true> : (const void*)ql::eval_kernel<ql::JM_NONE, false>;
+    if (fast) return ragged ? (const void*)ql::eval_kernel<JM, true, true> : (const void*)ql::eval_kernel<JM, true, false>;
+    return ragged ? (const void*)ql::eval_kernel<JM, false, true> : (const void*)ql::eval_kernel<JM, false, false>;
+}
+// ragged: rows addressed through offset tables (qlnlp_eval_ragged_device) instead of leading dimensions
+const void* kernel_fn(int jm, bool fast, bool ragged)
+{
+    if (jm == ql::JM_BLOCK) return kernel_fn_jm<ql::JM_BLOCK>(fast, ragged);
+    if (jm == ql::JM_TRUE) return kernel_fn_jm<ql::JM_TRUE>(fast, ragged);
+    return kernel_fn_jm<ql::JM_NONE>(fast, ragged);
 }
 
 // the sparse pattern batched evaluations of this handle produce (DENSE handles batch in SPARSE_BLOCK)
@@ -251,7 +258,8 @@ int ensure_device(qlnlp_handle h)
         if (h->smem[wj] > (size_t)prop.sharedMemPerBlockOptin)
             return fail(QLNLP_EINVAL, "N=%d needs %zu B of shared memory per warp (> %zu)", h->cls.N, h->smem[wj],
                         (size_t)prop.sharedMemPerBlockOptin);
-        const void* fn = kernel_fn(wj, h->fastdiv);
+      for (int rg = 0; rg < 2; ++rg) {
+        const void* fn = kernel_fn(wj, h->fastdiv, rg != 0);
         // the attribute is per FUNCTION, shared by every handle of the process: always raise it to the device
         // limit, never to this handle's own (possibly smaller) requirement
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
@@ -263,7 +271,8 @@ int ensure_device(qlnlp_handle h)
             const int cap = std::atoi(e);
             if (cap >= 1 && cap < nb) nb = cap;
         }
-        h->blocks_per_sm[wj] = nb;
+        h->blocks_per_sm[wj] = rg ? std::min(h->blocks_per_sm[wj], nb) : nb;
+      }
     }
     for (auto& ln : h->lanes) {
         CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
@@ -276,17 +285,23 @@ int ensure_device(qlnlp_handle h)
     return QLNLP_OK;
 }
 
-int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t stream, int jm_force = -1)
+int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t stream, int jm_force = -1,
+           const qlnlp_ragged_io* rg = nullptr)
 {
     const QlClass& c = h->cls;
     if (B < 0) return fail(QLNLP_EINVAL, "negative batch");
     if (!io || !io->Z) return fail(QLNLP_EINVAL, "io->Z is required");
+    if (rg) {
+        if (!rg->z_off || (io->g && !rg->g_off) || (io->jac && !rg->jac_off))
+            return fail(QLNLP_EINVAL, "ragged launch: offset tables are required for every requested array");
+    } else {
     if (io->ldz < c.n_nlp) return fail(QLNLP_EINVAL, "ldz %lld < n_nlp %d", (long long)io->ldz, c.n_nlp);
     if (io->grad && io->ldgrad < c.n_nlp) return fail(QLNLP_EINVAL, "ldgrad %lld < n_nlp %d", (long long)io->ldgrad, c.n_nlp);
     if (io->g && io->ldg < c.m_nlp) return fail(QLNLP_EINVAL, "ldg %lld < m_nlp %d", (long long)io->ldg, c.m_nlp);
+    }
     const int jm_jac = jm_force >= 0 ? jm_force : batch_jm(h);
     const int nnz_jac = jm_jac == ql::JM_TRUE ? c.nnz_true : c.nnz;
-    if (io->jac && io->ldjac < nnz_jac) return fail(QLNLP_EINVAL, "ldjac %lld < nnz %d", (long long)io->ldjac, nnz_jac);
+    if (!rg && io->jac && io->ldjac < nnz_jac) return fail(QLNLP_EINVAL, "ldjac %lld < nnz %d", (long long)io->ldjac, nnz_jac);
     if ((reinterpret_cast<uintptr_t>(io->Z) & 7) != 0) return fail(QLNLP_EINVAL, "Z must be 8-byte aligned");
     if (B == 0) return QLNLP_OK;
 
@@ -307,8 +322,13 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     P.g = io->g; P.ldg = io->ldg;
     P.jac = io->jac; P.ldjac = io->ldjac;
     P.B = B;
-    P.bulk = (io->jac && (reinterpret_cast<uintptr_t>(io->jac) & 15) == 0 && (io->ldjac & 1) == 0) ? 1 : 0;
-    P.zbulk = ((reinterpret_cast<uintptr_t>(io->Z) & 15) == 0 && (io->ldz & 1) == 0) ? 1 : 0;   // ldz even > n_nlp (odd)
+    P.index = rg ? reinterpret_cast<const long long*>(rg->index) : nullptr;
+    P.z_off = rg ? reinterpret_cast<const long long*>(rg->z_off) : nullptr;
+    P.g_off = rg ? reinterpret_cast<const long long*>(rg->g_off) : nullptr;
+    P.j_off = rg ? reinterpret_cast<const long long*>(rg->jac_off) : nullptr;
+    P.bulk = (io->jac && (reinterpret_cast<uintptr_t>(io->jac) & 15) == 0 && (rg || (io->ldjac & 1) == 0)) ? 1 : 0;
+    if (rg) P.zbulk = ((reinterpret_cast<uintptr_t>(io->Z) & 15) == 0 && (rg->flags & QLNLP_RAGGED_Z_PADDED)) ? 1 : 0;
+    else P.zbulk = ((reinterpret_cast<uintptr_t>(io->Z) & 15) == 0 && (io->ldz & 1) == 0) ? 1 : 0;   // ldz even > n_nlp (odd)
 
     const int wj = io->jac ? jm_jac : ql::JM_NONE;
     // Resident warps per SM.  The SPARSE_BLOCK stream is store-bound and the memory system takes the output of a
@@ -335,7 +355,7 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     }
     P.ticket = it->second;
     void* args[] = {&P};
-    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj, h->fastdiv), dim3(grid), dim3(QL_LANES), args, h->smem[wj], stream));
+    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj, h->fastdiv, rg != nullptr), dim3(grid), dim3(QL_LANES), args, h->smem[wj], stream));
     h->last_launch[0] = grid;
     h->last_launch[1] = QL_LANES;
     h->last_launch[2] = (int64_t)h->smem[wj];
@@ -659,6 +679,14 @@ int qlnlp_eval_batch_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io,
     if (int rc = check_handle(h)) return rc;
     if (int rc = ensure_device(h)) return rc;
     return launch(h, B, io, static_cast<cudaStream_t>(stream));
+}
+
+int qlnlp_eval_ragged_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, const qlnlp_ragged_io* rg, void* stream)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!rg) return fail(QLNLP_EINVAL, "null ragged descriptor");
+    if (int rc = ensure_device(h)) return rc;
+    return launch(h, B, io, static_cast<cudaStream_t>(stream), -1, rg);
 }
 
 int qlnlp_eval_batch_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)

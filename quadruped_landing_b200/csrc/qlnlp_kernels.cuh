@@ -160,6 +160,12 @@ struct Launch {
     double* g; long long ldg;
     double* jac; long long ldjac;
     long long B;
+    // RAGGED instantiation only: the b-th evaluation of the launch is problem index[b] (or b) of a flat, mixed-size
+    // batch; its rows start at Z + z_off[i], grad + z_off[i], g + g_off[i], jac + j_off[i]; f, x0, xf are indexed by i
+    const long long* index;
+    const long long* z_off;
+    const long long* g_off;
+    const long long* j_off;
     unsigned* ticket;          // [0] next evaluation to hand out, [1] CTAs that have finished (both 0 between launches)
     int bulk;                  // 1: jac rows are 16 B aligned -> TMA bulk stores
     int zbulk;                 // 1: Z rows are 16 B aligned and ldz > n_nlp -> one TMA bulk load per vector
@@ -195,7 +201,7 @@ __device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigne
     }
 }
 
-template <int JM, bool FASTDIV>
+template <int JM, bool FASTDIV, bool RAGGED>
 __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) eval_kernel(const __grid_constant__ Launch P)
 {
     constexpr bool WITH_JAC = JM != JM_NONE;
@@ -216,7 +222,11 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
     K.g = c.g; K.mb = c.mb; K.mf = c.mf; K.Ib = c.Ib; K.rmb = P.rmb; K.rmf = P.rmf; K.rIb = P.rIb;
     const bool first_is_y1 = (c.init_mode == 1);    // contact-first reads y1 (mode 1) or y2 (mode 2)
 
-    const bool zbulk = P.zbulk != 0;
+    const bool zbulk = P.zbulk != 0;      // ragged launches: only when the caller guarantees aligned, padded Z rows
+    auto zrow_of = [&](long long t) -> const double* {
+        if (RAGGED) return P.Z + __ldg(P.z_off + (P.index ? __ldg(P.index + t) : t));
+        return P.Z + t * P.ldz;
+    };
     unsigned zphase = 0;                 // parity of the mbarrier phase the next wait completes
     if (zbulk) {
         if (lane == 0) mbar_init(mbar, 1);
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
     };
     long long b = take();
     long long nb = P.B;
-    if (b < P.B) stage_z(P.Z + b * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
+    if (b < P.B) stage_z(zrow_of(b), zaddr, mbar, c.n_nlp, lane, zbulk);
     if (JM == JM_BLOCK) {
         // the segment plan lives in shared memory: one 16-byte record per segment
         const int4* src = reinterpret_cast<const int4*>(P.segs);
@@ -247,8 +257,12 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
         else cp_async_wait_all();
         __syncwarp();
         double fsum = 0.0;
-        double* const grow = P.g ? P.g + b * P.ldg : nullptr;
-        double* const gradrow = P.grad ? P.grad + b * P.ldgrad : nullptr;
+        const long long pi = (RAGGED && P.index) ? __ldg(P.index + b) : b;      // problem number (f, x0, xf, offsets)
+        double* const grow = P.g ? P.g + (RAGGED ? __ldg(P.g_off + pi) : b * P.ldg) : nullptr;
+        double* const gradrow = P.grad ? P.grad + (RAGGED ? __ldg(P.z_off + pi) : b * P.ldgrad) : nullptr;
+        double* const jrow = WITH_JAC ? P.jac + (RAGGED ? __ldg(P.j_off + pi) : b * P.ldjac) : nullptr;
+        // TMA bulk stores need 16-byte aligned rows: a launch-wide property for strided batches, per row when ragged
+        const bool bulk = P.bulk != 0 && (!RAGGED || (reinterpret_cast<uintptr_t>(jrow) & 15) == 0);
 
         for (int p = 0; p < c.npass; ++p) {
             const int k = p * QL_LANES + lane + 1;          // 1-based knot of this lane
@@ -351,12 +365,12 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                     if (k >= c.k_trans) grow[c.c_cother + (k - c.k_trans)] = first_is_y1 ? xk[6] : xk[4];      // :84/:86
                     grow[c.c_body + (k - 1)] = __dsub_rn(xk[1], __dmul_rn(c.half_lb, fabs(s)));                 // :109
                     if (k == 1) {
-                        const double* x0 = P.x0 ? P.x0 + b * QL_NX : P.x0_def;
+                        const double* x0 = P.x0 ? P.x0 + pi * QL_NX : P.x0_def;
 #pragma unroll
                         for (int i = 0; i < QL_NX; ++i) grow[i] = __dsub_rn(xk[i], __ldg(x0 + i));        // :149
                     }
                     if (k == c.N) {
-                        const double* xf = P.xf ? P.xf + b * QL_NX : P.xf_def;
+                        const double* xf = P.xf ? P.xf + pi * QL_NX : P.xf_def;
 #pragma unroll
                         for (int i = 0; i < QL_NX - 1; ++i) grow[c.c_term + i] = __dsub_rn(xk[i], __ldg(xf + i));   // :150
                     }
@@ -376,13 +390,12 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
             if (p == c.npass - 1) {
                 // zbuf is dead: prefetch the next decision vector while the Jacobian values stream out
                 nb = take();
-                if (nb < P.B) stage_z(P.Z + nb * P.ldz, zaddr, mbar, c.n_nlp, lane, zbulk);
+                if (nb < P.B) stage_z(zrow_of(nb), zaddr, mbar, c.n_nlp, lane, zbulk);
             }
 
             // ---- 5'. SPARSE_TRUE: every lane writes its whole run; the pass leaves as two bulk stores of 16 knots
             // (a half-pass staging buffer keeps the shared memory per warp small enough for 8 warps per SM)
             if (JM == JM_TRUE) {
-                double* const jrow = P.jac + b * P.ldjac;
                 for (int half = 0; half < 2; ++half) {
                     const int k_first = p * QL_LANES + 16 * half + 1;
                     if (k_first > c.N) break;
@@ -390,11 +403,11 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                     const int start = ql_true_run_off(c, k_first);
                     const int end = (k_end > c.N) ? c.nnz_true : ql_true_run_off(c, k_end);
                     const int base = start & ~1;
-                    if (P.bulk && lane == 0) bulk_wait_read<0>();       // the previous store has read the buffer
+                    if (P.bulk && lane == 0) bulk_wait_read<0>();     // the previous store has read the buffer
                     __syncwarp();
                     if (act && (lane >> 4) == half)
                         ql_true_write_run(c, k, jv, jtheta, jaddr + 8u * (unsigned)(ql_true_run_off(c, k) - base));
-                    if (P.bulk) {
+                    if (bulk) {
                         fence_proxy_async();
                         __syncwarp();
                         const int a = (start + 1) & ~1, e = end & ~1;
@@ -414,7 +427,6 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
 
             // ---- 5. SPARSE_BLOCK: stream this pass's share of the Jacobian values
             if (JM == JM_BLOCK) {
-                double* const jrow = P.jac + b * P.ldjac;
                 const int roff = act ? ql_run_off(c, k) : 0;
                 const int e4 = ql_e4(c, k), e6 = ql_e6(c, k), fc = ql_fc(c, k);
                 const int sb = __ldg(P.seg_begin + p), se = __ldg(P.seg_begin + p + 1);
@@ -438,7 +450,8 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                     pg[6] = raddr + 8u * (2 + e4 + e6 + 2 * fc);
 
                     // the bulk store issued two segments ago read this buffer: wait until it is done
-                    if (P.bulk && lane == 0) bulk_wait_read<1>();
+                    // (a ragged launch mixes bulk and plain rows: a plain row commits no groups, so it waits for all)
+                    if (P.bulk && lane == 0) { if (bulk) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
                     __syncwarp();
 
                     if ((bi ? tmpl1 : tmpl0) != tm) {            // different constant image: rebuild
@@ -464,7 +477,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                         }
                         st_shared_f64(raddr + 8u * (unsigned)ql_theta_pos(c, k), jtheta);   // constraints.jl:269-273
                     }
-                    if (P.bulk) {
+                    if (bulk) {
                         fence_proxy_async();
                         __syncwarp();
                         const int a = (start + 1) & ~1, e = end & ~1;      // 16 B aligned interior
@@ -486,7 +499,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
         if (P.f) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, off);
-            if (lane == 0) P.f[b] = fsum;
+            if (lane == 0) P.f[pi] = fsum;
         }
     }
     if (WITH_JAC && P.bulk && lane == 0) bulk_wait_all();

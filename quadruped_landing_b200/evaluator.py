@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "qlnlp_version", "qlnlp_last_error", "qlnlp_create", "qlnlp_destroy", "qlnlp_dims",
     "qlnlp_jacobian_structure", "qlnlp_constraint_bounds", "qlnlp_variable_bounds",
     "qlnlp_eval_objective", "qlnlp_eval_objective_gradient", "qlnlp_eval_constraint",
-    "qlnlp_eval_constraint_jacobian", "qlnlp_eval_batch_device", "qlnlp_eval_batch_host",
+    "qlnlp_eval_constraint_jacobian", "qlnlp_eval_batch_device", "qlnlp_eval_ragged_device", "qlnlp_eval_batch_host",
     "qlnlp_launch_info",
 )
 
@@ -58,6 +58,11 @@ class _BatchIO(C.Structure):
                 ("grad", C.c_void_p), ("ldgrad", C.c_int64),
                 ("g", C.c_void_p), ("ldg", C.c_int64),
                 ("jac", C.c_void_p), ("ldjac", C.c_int64)]
+
+
+class _RaggedIO(C.Structure):
+    _fields_ = [("index", C.c_void_p), ("z_off", C.c_void_p), ("g_off", C.c_void_p), ("jac_off", C.c_void_p),
+                ("flags", C.c_int64)]
 
 
 _lib = None
@@ -90,6 +95,7 @@ def load_library(rebuild_if_stale: bool = True):
                  "qlnlp_eval_constraint_jacobian"):
         getattr(L, name).argtypes = [vp, vp, vp]
     L.qlnlp_eval_batch_device.argtypes = [vp, C.c_int64, C.POINTER(_BatchIO), vp]
+    L.qlnlp_eval_ragged_device.argtypes = [vp, C.c_int64, C.POINTER(_BatchIO), C.POINTER(_RaggedIO), vp]
     L.qlnlp_eval_batch_host.argtypes = [vp, C.c_int64, C.POINTER(_BatchIO)]
     L.qlnlp_launch_info.argtypes = [vp, i64p]
     L.qlnlp_debug_segments.argtypes = [vp, vp, C.c_int64, i64p]
@@ -310,6 +316,33 @@ class HybridNLP:
         s = torch.cuda.current_stream(dev) if stream is None else stream
         _check(load_library().qlnlp_eval_batch_device(self._h, B, C.byref(io), C.c_void_p(s.cuda_stream)))
         return out
+
+    def eval_ragged(self, index, flat: Dict[str, "object"], offsets: Dict[str, "object"], *, x0=None, xf=None,
+                    stream=None, z_padded: bool = False) -> None:
+        """Evaluate the problems ``index`` (int64 CUDA tensor of problem numbers) of a flat, mixed-size batch.
+
+        ``flat`` holds the flat float64 CUDA tensors ``Z`` and any of ``f`` (indexed by problem number), ``grad``,
+        ``g``, ``jac``; ``offsets`` the int64 CUDA tensors ``z_off``, ``g_off``, ``j_off`` (start of every problem's
+        rows, in doubles).  Outputs are written in place; nothing is copied or gathered.  Not synchronised."""
+        import torch
+
+        B = int(index.shape[0])
+        io = _BatchIO()
+        io.Z = flat["Z"].data_ptr()
+        for name in ("f", "grad", "g", "jac"):
+            if flat.get(name) is not None:
+                setattr(io, name, flat[name].data_ptr())
+        if x0 is not None:
+            io.x0 = x0.data_ptr()
+        if xf is not None:
+            io.xf = xf.data_ptr()
+        rg = _RaggedIO(index.data_ptr(), offsets["z_off"].data_ptr(),
+                       offsets["g_off"].data_ptr() if flat.get("g") is not None else None,
+                       offsets["j_off"].data_ptr() if flat.get("jac") is not None else None,
+                       1 if z_padded else 0)
+        dev = flat["Z"].device
+        s = torch.cuda.current_stream(dev) if stream is None else stream
+        _check(load_library().qlnlp_eval_ragged_device(self._h, B, C.byref(io), C.byref(rg), C.c_void_p(s.cuda_stream)))
 
     def eval_batch_host(self, Z: np.ndarray, *, x0: Optional[np.ndarray] = None, xf: Optional[np.ndarray] = None,
                         want: Sequence[str] = ("f", "grad", "g", "jac"),

@@ -28,14 +28,28 @@ class RaggedEvaluator:
         self._streams = None
 
     def offsets(self, class_of: np.ndarray) -> Dict[str, np.ndarray]:
-        """Exclusive prefix sums: problem b owns Z[z_off[b]:z_off[b+1]], g[g_off[b]:...], jac[j_off[b]:...]."""
+        """Row starts (in doubles): problem b owns Z[z_off[b] : z_off[b] + n_b], g[g_off[b] : ...], jac[j_off[b] : ...].
+        Every row is padded to an even length, so all rows are 16-byte aligned (TMA load / store paths); the last
+        entry of each table is the total length to allocate."""
         class_of = np.asarray(class_of, dtype=np.int64)
-        cs = lambda w: np.concatenate([[0], np.cumsum(w[class_of])])
+        even = lambda w: (w + 1) & ~1
+        cs = lambda w: np.concatenate([[0], np.cumsum(even(w)[class_of])])
         return {"z_off": cs(self.n), "g_off": cs(self.m), "j_off": cs(self.nnz)}
+
+    def pack(self, class_of: np.ndarray, vectors) -> np.ndarray:
+        """Lay decision vectors (one per problem) out in the padded flat Z layout of ``offsets``."""
+        off = self.offsets(class_of)["z_off"]
+        Z = np.zeros(int(off[-1]))
+        for b, v in enumerate(vectors):
+            Z[off[b]:off[b] + len(v)] = v
+        return Z
 
     def eval(self, class_of: np.ndarray, Z_flat, want=("f", "grad", "g", "jac")):
         """``Z_flat``: 1-D float64 CUDA tensor holding the decision vectors back to back (see ``offsets``).
-        Returns flat CUDA tensors ``f[B]``, ``grad`` (Z layout), ``g``, ``jac`` and the offset tables."""
+        Returns flat CUDA tensors ``f[B]``, ``grad`` (Z layout), ``g``, ``jac`` and the offset tables.
+
+        Every class is one ``qlnlp_eval_ragged_device`` launch on its own stream: the kernel addresses each
+        problem's rows through the offset tables, so nothing is gathered or scattered."""
         import torch
 
         class_of = np.asarray(class_of, dtype=np.int64)
@@ -44,15 +58,16 @@ class RaggedEvaluator:
         dev = Z_flat.device
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=dev) for _ in self.nlps]
-        out = {}
+        flat = {"Z": Z_flat}
         if "f" in want:
-            out["f"] = torch.empty(B, dtype=torch.float64, device=dev)
+            flat["f"] = torch.empty(B, dtype=torch.float64, device=dev)
         if "grad" in want:
-            out["grad"] = torch.empty(int(off["z_off"][-1]), dtype=torch.float64, device=dev)
+            flat["grad"] = torch.empty(int(off["z_off"][-1]), dtype=torch.float64, device=dev)
         if "g" in want:
-            out["g"] = torch.empty(int(off["g_off"][-1]), dtype=torch.float64, device=dev)
+            flat["g"] = torch.empty(int(off["g_off"][-1]), dtype=torch.float64, device=dev)
         if "jac" in want:
-            out["jac"] = torch.empty(int(off["j_off"][-1]), dtype=torch.float64, device=dev)
+            flat["jac"] = torch.empty(int(off["j_off"][-1]), dtype=torch.float64, device=dev)
+        doff = {k: torch.from_numpy(v).to(dev) for k, v in off.items()}
         cur = torch.cuda.current_stream(dev)
         keep = []
         for c, nlp in enumerate(self.nlps):
@@ -62,20 +77,11 @@ class RaggedEvaluator:
             s = self._streams[c]
             s.wait_stream(cur)
             with torch.cuda.stream(s):
-                def rows(offs, width):
-                    base = torch.from_numpy(offs[idx]).to(dev)
-                    return base[:, None] + torch.arange(width, device=dev)[None, :]
-                zi = rows(off["z_off"], nlp.n_nlp)
-                res = nlp.eval_batch(Z_flat[zi], want=want)
-                if "f" in want:
-                    out["f"][torch.from_numpy(idx).to(dev)] = res["f"]
-                if "grad" in want:
-                    out["grad"][zi] = res["grad"]
-                if "g" in want:
-                    out["g"][rows(off["g_off"], nlp.m_nlp)] = res["g"]
-                if "jac" in want:
-                    out["jac"][rows(off["j_off"], nlp.nnz_block)] = res["jac"]
-                keep.append(res)
+                index = torch.from_numpy(idx).to(dev)
+                nlp.eval_ragged(index, flat, doff, stream=s, z_padded=True)
+                keep.append(index)
             cur.wait_stream(s)
+        out = {k: v for k, v in flat.items() if k != "Z"}
         out.update(off)
+        self._keep = (keep, doff)          # alive until the next call: the launches are asynchronous
         return out

@@ -242,21 +242,24 @@ def test_c4_ragged_batch_of_mixed_horizons():
     class_of = rng.integers(0, len(classes), size=B)
     off = ev.offsets(class_of)
     guesses = [ql.initial_guess(p) for p in probs]
-    Zf = np.concatenate([guesses[c] for c in class_of]) + 1e-2 * rng.standard_normal(int(off["z_off"][-1]))
-    for b in range(B):                                     # clip the h entries like the other configs
-        seg = Zf[off["z_off"][b]:off["z_off"][b + 1]]
-        seg[19::20] = np.clip(seg[19::20], 1e-3, 2e-2)
+    vecs = []
+    for b in range(B):
+        v = guesses[class_of[b]] + 1e-2 * rng.standard_normal(probs[class_of[b]].n_nlp)
+        v[19::20] = np.clip(v[19::20], 1e-3, 2e-2)         # clip the h entries like the other configs
+        vecs.append(v)
+    Zf = ev.pack(class_of, vecs)                           # rows padded to an even length: all 16-byte aligned
     out = ev.eval(class_of, torch.from_numpy(Zf).cuda())
     torch.cuda.synchronize()
     oracles = [Oracle(p) for p in probs]
     for b in range(0, B, 37):
         c = class_of[b]
-        z = Zf[off["z_off"][b]:off["z_off"][b + 1]]
+        e = ev.nlps[c]
+        z = vecs[b]
         ref = oracles[c].eval_batch(z[None, :])
         got = {"f": out["f"][b:b + 1].cpu().numpy(),
-               "grad": out["grad"][off["z_off"][b]:off["z_off"][b + 1]].cpu().numpy()[None, :],
-               "g": out["g"][off["g_off"][b]:off["g_off"][b + 1]].cpu().numpy()[None, :],
-               "jac": out["jac"][off["j_off"][b]:off["j_off"][b + 1]].cpu().numpy()[None, :]}
+               "grad": out["grad"][off["z_off"][b]:off["z_off"][b] + e.n_nlp].cpu().numpy()[None, :],
+               "g": out["g"][off["g_off"][b]:off["g_off"][b] + e.m_nlp].cpu().numpy()[None, :],
+               "jac": out["jac"][off["j_off"][b]:off["j_off"][b] + e.nnz_block].cpu().numpy()[None, :]}
         assert_same_bits(ev.nlps[c], got, ref, f"problem {b} class {classes[c]}: ")
 
 

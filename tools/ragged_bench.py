@@ -1,0 +1,27 @@
+"""32,768 problems of 12 mixed classes in flat arrays; throughput of the ragged path."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import quadruped_landing_b200 as ql
+classes = [(N, kt, im) for (N, kt) in [(31, 11), (41, 14), (61, 21), (81, 27), (101, 34), (121, 41)] for im in (1, 2)]
+probs = [ql.build_problem(N=N, k_trans=kt, init_mode=im) for N, kt, im in classes]
+ev = ql.RaggedEvaluator(probs)
+rng = np.random.default_rng(7)
+B = 32768
+class_of = rng.integers(0, len(classes), size=B)
+off = ev.offsets(class_of)
+guesses = [ql.initial_guess(p) for p in probs]
+Zf = ev.pack(class_of, [guesses[c] + 1e-2 * rng.standard_normal(probs[c].n_nlp) for c in class_of])
+Zd = torch.from_numpy(Zf).cuda()
+out = ev.eval(class_of, Zd); torch.cuda.synchronize()
+bytes_total = 8 * (2 * int(off["z_off"][-1]) + int(off["g_off"][-1]) + int(off["j_off"][-1]) + B)
+for _ in range(2):
+    ev.eval(class_of, Zd)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+n = 5
+for _ in range(n):
+    ev.eval(class_of, Zd)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / n
+print(f"C4 ragged: B={B}, {bytes_total / 1e9:.2f} GB per pass, {dt * 1e3:.2f} ms  {B / dt / 1e6:.2f} M evals/s  {bytes_total / dt / 1e12:.2f} TB/s (includes per-call output allocation)")
