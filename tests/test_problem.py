@@ -64,3 +64,22 @@ def test_solution_csv_round_trip(tmp_path, golden):
     tab = ql.solution_table(golden["data_6"], 61)
     assert tab.shape == (61, 20) and tab[60, 14] == 0.848539898959304 and not tab[60, 15:].any()
     assert tab[59, 16] + tab[59, 18] == 98.10000000000001                            # plot_data.py columns 15-18 = forces
+
+
+def test_ragged_offsets_are_aligned_and_pack_round_trips():
+    """Host logic of the ragged path (no GPU needed): rows are padded to an even length so every row of the flat
+    arrays starts 16-byte aligned; pack() places the vectors at z_off."""
+    probs = [ql.build_problem(N=N, k_trans=kt, init_mode=im) for N, kt, im in [(31, 11, 1), (41, 14, 2), (61, 21, 1)]]
+    ev = ql.RaggedEvaluator(probs)
+    rng = np.random.default_rng(0)
+    class_of = rng.integers(0, 3, size=50)
+    off = ev.offsets(class_of)
+    for key, widths in (("z_off", ev.n), ("g_off", ev.m), ("j_off", ev.nnz)):
+        o = off[key]
+        assert o[0] == 0 and np.all(o % 2 == 0)
+        assert np.all(np.diff(o) >= widths[class_of]) and np.all(np.diff(o) - widths[class_of] <= 1)
+    vecs = [rng.normal(size=probs[c].n_nlp) for c in class_of]
+    Z = ev.pack(class_of, vecs)
+    assert Z.shape == (off["z_off"][-1],)
+    for b, v in enumerate(vecs):
+        assert np.array_equal(Z[off["z_off"][b]:off["z_off"][b] + len(v)], v)
