@@ -109,7 +109,9 @@ int qlnlp_eval_constraint_jacobian(qlnlp_handle h, const double* x, double* vals
 
 /* ---- batched evaluation (B independent decision vectors; no reference equivalent) -------- */
 typedef struct {
-    const double* Z;   int64_t ldz;     /* [B][ldz],    ldz    >= n_nlp          (required) */
+    const double* Z;   int64_t ldz;     /* [B][ldz],    ldz    >= n_nlp          (required).  With Z 16-byte aligned
+                                           and ldz even (> n_nlp, which is odd) a row is fetched with one TMA load that
+                                           also READS the padding element Z[b][n_nlp]. */
     const double* x0;                   /* [B][15] per-evaluation initial state, or NULL -> desc.x0 */
     const double* xf;                   /* [B][15] per-evaluation final state,   or NULL -> desc.xf */
     double* f;                          /* [B]                                    or NULL: skip */
@@ -147,7 +149,8 @@ int qlnlp_eval_ragged_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io
 
 /* All pointers are HOST pointers.  Copies Z (and x0/xf) to the device, evaluates, copies the
  * requested outputs back, and returns when they are in place.  Work is pipelined in chunks over
- * two streams so copies overlap the kernel. */
+ * two streams so copies overlap the kernel.  SPARSE_BLOCK rows of batches >= 64 cross PCIe as their structural
+ * non-zeros and are rebuilt in the caller's buffer by host threads (identical rows, no host arithmetic). */
 int qlnlp_eval_batch_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io);
 
 /* Launch geometry of the last batched launch (for benchmarks / profiles): blocks, threads per
