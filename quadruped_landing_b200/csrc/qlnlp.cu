@@ -43,6 +43,8 @@ int fail(int code, const char* fmt, ...)
                         cudaGetErrorString(e_), __FILE__, __LINE__);                                \
     } while (0)
 
+constexpr int TICKET_POOL = 64;
+
 // per-stream scratch of the host-pointer pipeline
 struct HostLane {
     cudaStream_t stream = nullptr;
@@ -80,6 +82,8 @@ struct qlnlp_handle_s {
     int64_t last_launch[5] = {0, 0, 0, 0, 0};
     HostLane lanes[2];
     std::map<cudaStream_t, unsigned*> tickets;   // work counters, one pair per stream the handle has launched on
+    unsigned* ticket_pool = nullptr;             // pre-zeroed counters (128 B apart) so that a launch needs no
+    int ticket_pool_used = 0;                    // allocation: launches stay legal inside CUDA-graph capture
     std::vector<int32_t> true2block;   // position of every SPARSE_TRUE value inside a SPARSE_BLOCK row
     int64_t ldz_e = 0, ldgrad_e = 0, ldg_e = 0, ldjac_e = 0;   // even leading dimensions of the scratch
 };
@@ -278,6 +282,8 @@ int ensure_device(qlnlp_handle h)
         CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
     }
+    CUDA_TRY(cudaMalloc(&h->ticket_pool, 128 * TICKET_POOL));
+    CUDA_TRY(cudaMemset(h->ticket_pool, 0, 128 * TICKET_POOL));
     // the set-up copies above ran on the legacy default stream and may still be in flight when cudaMemcpy returns
     // (pageable source); launches go to arbitrary, possibly non-blocking streams, so finish the set-up first
     CUDA_TRY(cudaDeviceSynchronize());
@@ -347,10 +353,14 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     auto it = h->tickets.find(stream);
     if (it == h->tickets.end()) {
         unsigned* d = nullptr;
-        CUDA_TRY(cudaMalloc(&d, 128));
-        // zero it ON THIS STREAM: cudaMemset on device memory is asynchronous (legacy default stream) and would
-        // not be ordered before a launch on a non-blocking stream
-        CUDA_TRY(cudaMemsetAsync(d, 0, 128, stream));
+        if (h->ticket_pool_used < TICKET_POOL) {
+            d = h->ticket_pool + 32 * h->ticket_pool_used++;      // zeroed (and synchronised) at set-up
+        } else {
+            CUDA_TRY(cudaMalloc(&d, 128));
+            // zero it ON THIS STREAM: cudaMemset on device memory is asynchronous (legacy default stream) and would
+            // not be ordered before a launch on a non-blocking stream
+            CUDA_TRY(cudaMemsetAsync(d, 0, 128, stream));
+        }
         it = h->tickets.emplace(stream, d).first;
     }
     P.ticket = it->second;
@@ -610,7 +620,9 @@ int qlnlp_destroy(qlnlp_handle h)
             if (ln.stream) cudaStreamDestroy(ln.stream);
             if (ln.done) cudaEventDestroy(ln.done);
         }
-        for (auto& kv : h->tickets) cudaFree(kv.second);
+        for (auto& kv : h->tickets)
+            if (kv.second < h->ticket_pool || kv.second >= h->ticket_pool + 32 * TICKET_POOL) cudaFree(kv.second);
+        cudaFree(h->ticket_pool);
         cudaFree(h->d_cost); cudaFree(h->d_x0xf); cudaFree(h->d_segs); cudaFree(h->d_seg_begin);
         cudaFree(h->d_dense_lin); cudaFree(h->d_dense);
     }

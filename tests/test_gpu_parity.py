@@ -426,3 +426,32 @@ def test_randomised_stress_against_the_oracle():
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "0 failures" in r.stdout
+
+
+def test_launches_can_be_captured_in_a_cuda_graph(dflt, golden):
+    """The launch path makes no allocation or synchronising call (work counters come from a pre-zeroed pool and
+    re-arm themselves), so a sequence of evaluations can be captured once and replayed as a CUDA graph."""
+    p, nlp, o = dflt
+    Z = perturbed_batch(p, _bases(p, golden), 600, 1e-2, 77)
+    Zd = torch.zeros((600, 1216), dtype=torch.float64, device="cuda")[:, :1215]
+    Zd.copy_(torch.from_numpy(Z))
+    eager = {k: v.clone() for k, v in nlp.eval_batch(Zd).items()}
+    torch.cuda.synchronize()
+    out = {k: torch.zeros_like(v) for k, v in eager.items()}
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # warm the capture stream's work counter outside the capture
+        nlp.eval_batch(Zd, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        nlp.eval_batch(Zd, out=out, want=("g", "jac"))
+        nlp.eval_batch(Zd, out=out, want=("f", "grad"))
+    for k in out:
+        out[k].zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    for k in eager:
+        assert torch.equal(out[k], eager[k]), k
