@@ -1,6 +1,6 @@
 """Randomised stress test of the CUDA path against the oracle: random problem classes, batch sizes, leading
 dimensions / alignments, output subsets, both sparse patterns, device and host entry points, canary rows.
-    python tools/fuzz_gpu.py [seconds] [seed]
+    python tests/fuzz_gpu.py [seconds] [seed]
 """
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

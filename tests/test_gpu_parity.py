@@ -417,12 +417,12 @@ def test_solver_loop_on_the_gpu_evaluator():
 
 
 def test_randomised_stress_against_the_oracle():
-    """tools/fuzz_gpu.py for 20 s: random classes (N in 2..121, any k_trans / init_mode), batch sizes 1..3000,
+    """tests/fuzz_gpu.py for 20 s: random classes (N in 2..121, any k_trans / init_mode), batch sizes 1..3000,
     paddings and alignments, output subsets, both sparse patterns, device and host entry points, canary rows.
     (A 150 s run of the same script covered 1176 cases without a failure.)"""
     import subprocess, sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_gpu.py"), "20", "7"], capture_output=True,
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_gpu.py"), "20", "7"], capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "0 failures" in r.stdout
