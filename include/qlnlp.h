@@ -13,6 +13,7 @@
  *   - indices handed to the caller are 1-BASED (Julia / MOI convention, moi.jl:31-33);
  *   - one handle may be driven by one host thread at a time (Ipopt calls back from one thread);
  *     different handles are independent;
+ *   - every call leaves the calling thread's current CUDA device as it found it;
  *   - there is NO CPU fallback: evaluation entry points fail with QLNLP_ENODEVICE when no
  *     sm_100 device / driver is present.  Structure, dimension and bound queries are pure host
  *     integer logic and work anywhere.
@@ -35,7 +36,7 @@
 extern "C" {
 #endif
 
-#define QLNLP_VERSION 1
+#define QLNLP_VERSION 2
 
 enum {
     QLNLP_OK = 0,
@@ -83,6 +84,25 @@ typedef struct qlnlp_handle_s* qlnlp_handle;
 int qlnlp_create(const qlnlp_problem_desc* desc, int device, int jac_mode, qlnlp_handle* out);
 int qlnlp_destroy(qlnlp_handle h);
 
+/* The same evaluator spread over several GPUs of one process (the problems are independent, so a batch
+ * is split into contiguous shards, qlnlp_shard_bounds, one per device, with no exchange between the devices).
+ * `devices` lists ndev distinct CUDA ordinals.  On such a handle
+ *   - qlnlp_eval_batch_host shards the caller's batch itself: one driver thread + one pipeline per device, and the
+ *     host cores are split between the devices;
+ *   - qlnlp_eval_batch_device_multi launches one shard per device on device-resident arrays;
+ *   - the single-evaluation callbacks and the integer queries use the first device;
+ *   - qlnlp_eval_batch_device / qlnlp_eval_ragged_device are refused (they take one device's pointers). */
+int qlnlp_create_multi(const qlnlp_problem_desc* desc, const int* devices, int ndev, int jac_mode, qlnlp_handle* out);
+/* devices of the handle (1 for qlnlp_create); fills at most cap ordinals */
+int qlnlp_devices(qlnlp_handle h, int* devices, int cap, int* ndev);
+/* shard `shard` of `nshards` covers evaluations [lo, hi): contiguous and balanced, the first B % nshards shards hold
+ * one extra evaluation */
+int qlnlp_shard_bounds(int64_t B, int nshards, int shard, int64_t* lo, int64_t* hi);
+/* tuning knobs: "host_chunk" (evaluations per pipeline stage of the host-pointer path, default 256), "host_threads"
+ * (row-builder threads per device, 0 = this handle's share of the CPUs the process may use), "pin_threads" (0/1),
+ * "x_cache" (0/1: serve repeated single-evaluation callbacks at the same x from the last evaluation) */
+int qlnlp_set_option(qlnlp_handle h, const char* name, int64_t value);
+
 /* num_primals / num_duals                                          nlp.jl:86-87
  * nnz = length of the structure for the handle's jac_mode; nnz_block = SPARSE_BLOCK count. */
 int qlnlp_dims(qlnlp_handle h, int64_t* n_nlp, int64_t* m_nlp, int64_t* nnz, int64_t* nnz_block);
@@ -96,7 +116,11 @@ int qlnlp_constraint_bounds(qlnlp_handle h, double* lb, double* ub);
 /* the variable bounds solve() installs                             moi.jl:51-67 */
 int qlnlp_variable_bounds(qlnlp_handle h, double* xl, double* xu);
 
-/* ---- single evaluations on HOST pointers: the four MOI callbacks ------------------------- */
+/* ---- single evaluations on HOST pointers: the four MOI callbacks -------------------------
+ * Ipopt asks for f, grad f, g and the Jacobian values of an iterate in separate callbacks.  The first callback at a
+ * new x evaluates all four with ONE launch (one H2D copy, one kernel, one D2H copy) and keeps the results; callbacks
+ * that follow with the same x (compared bit for bit; 9.7 KB at the default instance) are served from that cache, so
+ * a caller need not track Ipopt's new_x flag.  The evaluator keeps no other state between calls. */
 /* MOI.eval_objective(prob, x)               -> eval_f              moi.jl:1-3   costs.jl:6-16 */
 int qlnlp_eval_objective(qlnlp_handle h, const double* x, double* f);
 /* MOI.eval_objective_gradient(prob, grad, x) -> grad_f!            moi.jl:5-8   costs.jl:23-34 */
@@ -106,6 +130,8 @@ int qlnlp_eval_constraint(qlnlp_handle h, const double* x, double* g);
 /* MOI.eval_constraint_jacobian(prob, vals, x) -> jac_c!            moi.jl:15-24 constraints.jl:212-291
  * vals has qlnlp_dims().nnz entries in jacobian_structure order. */
 int qlnlp_eval_constraint_jacobian(qlnlp_handle h, const double* x, double* vals);
+/* all four at once (any output may be NULL): what the callbacks above do at a new x            moi.jl:1-24 */
+int qlnlp_eval_all(qlnlp_handle h, const double* x, double* f, double* grad, double* g, double* vals);
 
 /* ---- batched evaluation (B independent decision vectors; no reference equivalent) -------- */
 typedef struct {
@@ -147,11 +173,37 @@ typedef struct {
 #define QLNLP_RAGGED_Z_PADDED 1
 int qlnlp_eval_ragged_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, const qlnlp_ragged_io* rg, void* stream);
 
-/* All pointers are HOST pointers.  Copies Z (and x0/xf) to the device, evaluates, copies the
- * requested outputs back, and returns when they are in place.  Work is pipelined in chunks over
- * two streams so copies overlap the kernel.  SPARSE_BLOCK rows of batches >= 64 cross PCIe as their structural
- * non-zeros and are rebuilt in the caller's buffer by host threads (identical rows, no host arithmetic). */
+/* One shard per device of a multi-device handle (or the single device of a plain one): B[i] evaluations on the
+ * DEVICE pointers of io[i], which live on device i of the handle, enqueued on streams[i] (NULL array or entry = that
+ * device's default stream).  Not synchronised; qlnlp_synchronize waits for every device of the handle. */
+int qlnlp_eval_batch_device_multi(qlnlp_handle h, const int64_t* B, const qlnlp_batch_io* io, void* const* streams);
+int qlnlp_synchronize(qlnlp_handle h);
+
+/* All pointers are HOST pointers.  Copies Z (and x0/xf) to the device, evaluates, copies the requested outputs back,
+ * and returns when they are in place.  Work is pipelined in chunks over three streams so copies overlap the kernel;
+ * pinned (page-locked) host arrays make the copies asynchronous (qlnlp_host_pin).  For batches >= 64 only the
+ * VALUE-DEPENDENT Jacobian entries cross PCIe (2,794 of the 32,161 SPARSE_BLOCK values at the default instance): a
+ * persistent pool of host threads assembles the caller's rows from the constant image of the pattern (zeros, +-1)
+ * and those entries, written a 64-byte line at a time with non-temporal stores -- identical rows, no host
+ * arithmetic.  On a multi-device handle the batch is split into one contiguous shard per device. */
 int qlnlp_eval_batch_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io);
+
+/* Registered output rows.  jac_c! itself assigns only part of the caller's matrix and relies on the rest of the
+ * buffer keeping its zeros (constraints.jl:212-291 never clears it).  A host caller that reuses one `jac` array
+ * for every batch can do the same here: qlnlp_host_output_register writes the constant image of the handle's
+ * pattern into the B rows once; later qlnlp_eval_batch_host calls whose io->jac points at a row of that buffer
+ * (same ldjac) rewrite only the 64-byte lines that hold a value-dependent entry (42 % of a SPARSE_BLOCK row at the
+ * default instance).  The caller must not overwrite the rows in between (reading them is fine); unregister, or
+ * register again, after doing so.  The resulting rows are identical to the unregistered ones. */
+int qlnlp_host_output_register(qlnlp_handle h, double* jac, int64_t ldjac, int64_t B);
+int qlnlp_host_output_unregister(qlnlp_handle h, double* jac);
+/* page-lock / unlock a caller-owned host array (cudaHostRegister) so that copies to and from it are asynchronous */
+int qlnlp_host_pin(void* ptr, int64_t bytes);
+int qlnlp_host_unpin(void* ptr);
+/* host path facts: [0] row-builder threads per device, [1] Jacobian doubles per evaluation that cross PCIe,
+ * [2] doubles per row, [3] 64-byte lines rewritten per registered row, [4] lines per row, [5] AVX-512 writer in use,
+ * [6] rows assembled so far, [7] lines written so far */
+int qlnlp_host_path_info(qlnlp_handle h, int64_t info[8]);
 
 /* Launch geometry of the last batched launch (for benchmarks / profiles): blocks, threads per
  * block, dynamic shared memory per block, resident blocks per SM, SM count. */

@@ -13,7 +13,18 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libqlnlp.so")
 SOURCES = ["qlnlp.cu"]
-HEADERS = ["layout.h", "qlnlp_kernels.cuh", "rk4_dual_gen.h", os.path.join("..", "..", "include", "qlnlp.h")]
+HOST_SOURCES = ["hostrows.cpp"]        # plain C++ (g++): worker pool + row builder of the host-pointer path
+
+
+def _deps():
+    """Every file the library is built from: all of csrc/ plus the public header (a glob, so the list cannot drift)."""
+    import glob
+    out = []
+    for pat in ("*.cu", "*.cuh", "*.h", "*.cpp"):
+        out += glob.glob(os.path.join(CSRC, pat))
+    out.append(os.path.join(_HERE, "..", "include", "qlnlp.h"))
+    out.append(os.path.abspath(__file__))
+    return out
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,8 +44,21 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def _host_objects(prefix: str):
+    """g++ -c of the plain C++ sources (the AVX-512 row writer sits behind a function-level target attribute, which
+    nvcc's front end does not accept)."""
+    objs = []
+    for src in HOST_SOURCES:
+        obj = f"{prefix}.{os.path.splitext(src)[0]}.o"
+        res = subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", os.path.join(CSRC, src), "-o", obj],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+        objs.append(obj)
+    return objs
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -51,11 +75,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not force and not is_stale():          # another process built it while we waited
             return LIB
         tmp = f"{LIB}.tmp.{os.getpid()}"
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+        objs = _host_objects(tmp)
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-Xcompiler", "-pthread", "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES] + objs
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
         res = subprocess.run(cmd, capture_output=True, text=True)
+        for o in objs:
+            os.unlink(o)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
         os.replace(tmp, LIB)
@@ -67,8 +94,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 def build_variant(name: str, defines) -> str:
     """Compile an experimental variant (extra -D flags) to libqlnlp_<name>.so for A/B timing (tools/ab_bench.py)."""
     out = os.path.join(_HERE, f"libqlnlp_{name}.so")
-    cmd = [nvcc_path(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    objs = _host_objects(out)
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-Xcompiler", "-pthread", *[f"-D{d}" for d in defines], "-o", out] + \
+          [os.path.join(CSRC, s) for s in SOURCES] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
+    for o in objs:
+        os.unlink(o)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     return out

@@ -36,6 +36,7 @@ struct QlClass {
     int N, k_trans, init_mode;            // 1-based meaning, as in HybridNLP (nlp.jl:16-19)
     int n_nlp, m_nlp, nnz;                // nlp.jl:72,63 ; entries jac_c! assigns (SPARSE_BLOCK)
     int nnz_true;                         // structurally non-zero entries (SPARSE_TRUE)
+    int nnz_vals;                         // value-dependent entries (VALS stream of the host path)
     int c_term, c_dyn, c_cfirst, c_cother, c_fctrl, c_body;   // 0-based first row of each g block (c_init = 0)
     int npass;                            // ceil(N / 32)
     double g, mb, mf, lb;                 // planar_quadruped.jl:11-20
@@ -63,6 +64,7 @@ QL_HD void ql_class_init(QlClass* c, int N, int k_trans, int init_mode,
     c->mbg = mb * g;
     c->half_lb = lb / 2;
     c->nnz_true = 0;                      // filled by ql_class_finish (needs the helpers below)
+    c->nnz_vals = 0;
 }
 
 // ---- per-knot extras -----------------------------------------------------------------------
@@ -179,7 +181,34 @@ QL_HD int ql_true_run_off(const QlClass& c, int k)
 }
 QL_HD int ql_true_nnz(const QlClass& c) { return ql_true_run_off(c, c.N) + QL_TRUE_LEN_LAST + 2 + ql_e4(c, c.N) + ql_e6(c, c.N); }
 
-QL_HD void ql_class_finish(QlClass* c) { c->nnz_true = ql_true_nnz(*c); }
+
+// ---- VALS: only the VALUE-DEPENDENT entries, column-major order (what changes between two evaluations of a
+// SPARSE_BLOCK / SPARSE_TRUE row: the jv entries of the RK4 block + the body-clearance d/dtheta entry).  This is
+// the stream host-pointer batches ship over PCIe; host threads merge it into the caller's rows (hostrows.cpp).
+// Per-knot counts come from rk4_dual_gen.h (QL_VALS_LEN_*; checked by static_assert in qlnlp_kernels.cuh).
+#define QL_VALS_LEN_INIT 56      // 55 jv + d/dtheta
+#define QL_VALS_LEN_JUMPK 49     // jump knot: the 7 entries of masked rows are constant zeros
+#define QL_VALS_LEN_M3 42        // 41 jv + d/dtheta
+#define QL_VALS_LEN_LAST 1       // knot N: d/dtheta only
+QL_HD int ql_vals_len(const QlClass& c, int k)
+{
+    if (k == c.N) return QL_VALS_LEN_LAST;
+    if (k >= c.k_trans) return QL_VALS_LEN_M3;
+    return k == c.k_trans - 1 ? QL_VALS_LEN_JUMPK : QL_VALS_LEN_INIT;
+}
+QL_HD int ql_vals_run_off(const QlClass& c, int k)
+{
+    const int km = k - 1;
+    const int kj = c.k_trans - 1;
+    int n_init = kj - 1; if (n_init < 0) n_init = 0; if (n_init > km) n_init = km;
+    const int n_jump = (kj >= 1 && kj <= km) ? 1 : 0;
+    int hi = km < c.N - 1 ? km : c.N - 1;
+    int n_m3 = hi - c.k_trans + 1; if (n_m3 < 0) n_m3 = 0;
+    return n_init * QL_VALS_LEN_INIT + n_jump * QL_VALS_LEN_JUMPK + n_m3 * QL_VALS_LEN_M3;
+}
+QL_HD int ql_vals_nnz(const QlClass& c) { return ql_vals_run_off(c, c.N) + QL_VALS_LEN_LAST; }
+
+QL_HD void ql_class_finish(QlClass* c) { c->nnz_true = ql_true_nnz(*c); c->nnz_vals = ql_vals_nnz(*c); }
 
 // ---- segments: what one bulk store moves ---------------------------------------------------
 // A segment is 1 or 2 consecutive knots of one pass.  Its image lives in a staging buffer at offset
@@ -190,7 +219,10 @@ struct QlSeg {
     int end;              // stream offset one past the last knot's run
     short k0;             // first knot (1-based)
     signed char nk;       // 1 or 2
-    signed char buf;      // staging buffer 0/1
+    signed char buf;      // unused (the kernel alternates buffers with a running counter, ql_seg_buffer)
     short tmpl;           // template id: equal ids <=> identical constant image
     short pad;
 };
+// staging buffer of the n-th segment a warp streams (n counts across evaluations): strict alternation, so the two
+// most recent bulk stores always come from different buffers whatever the number of segments per evaluation
+QL_HD int ql_seg_buffer(unsigned n) { return (int)(n & 1u); }

@@ -1,22 +1,22 @@
 // qlnlp.cu -- C ABI (include/qlnlp.h) over the fused evaluator kernel, plus the host-side planner
-// (segment plan, Jacobian structure, bounds).  Built with nvcc for sm_100a only; no CPU fallback.
+// (segment plan, Jacobian structure, bounds) and the host-pointer pipeline.  Built with nvcc for sm_100a only;
+// no CPU fallback: every evaluation entry point runs the CUDA kernels or fails.
 #include "../../include/qlnlp.h"
 
 #include <cuda_runtime.h>
-#if defined(__x86_64__)
-#include <emmintrin.h>      // _mm_stream_pd: rebuild host rows without read-for-ownership traffic
-#endif
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <new>
 #include <string>
-#include <thread>
 #include <vector>
 
+#include "hostrows.h"
 #include "layout.h"
 #include "qlnlp_kernels.cuh"
 
@@ -44,6 +44,24 @@ int fail(int code, const char* fmt, ...)
     } while (0)
 
 constexpr int TICKET_POOL = 64;
+constexpr int NJM = 4;                 // kernel value streams: JM_NONE, JM_BLOCK, JM_TRUE, JM_VALS
+constexpr int MAX_LANES = 3;           // pipeline depth of the host-pointer path
+constexpr int64_t COMPACT_MIN_B = 64;  // below this, host-pointer batches copy the pattern rows as they are
+
+// Every entry point that touches the device makes the handle's device current and restores the caller's on exit
+// (a multi-GPU host -- torch, CUDA.jl -- must not find its current device changed by a call into this library).
+struct DeviceGuard {
+    int prev = -1, dev;
+    explicit DeviceGuard(int d) : dev(d)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
 
 // per-stream scratch of the host-pointer pipeline
 struct HostLane {
@@ -51,7 +69,23 @@ struct HostLane {
     cudaEvent_t done = nullptr; // the chunk's last copy has landed
     int64_t cap = 0;            // evaluations the buffers hold
     double *Z = nullptr, *x0 = nullptr, *xf = nullptr, *f = nullptr, *grad = nullptr, *g = nullptr, *jac = nullptr;
-    double* stage = nullptr;    // pinned host rows of SPARSE_TRUE values awaiting expansion (compact transfer)
+    double* stage = nullptr;    // pinned host rows of VALS values awaiting the row builder
+};
+
+// single evaluations (the four MOI callbacks): one launch per decision vector, results cached
+struct OneEval {
+    cudaStream_t stream = nullptr;
+    double* hx = nullptr;       // pinned: x | f grad g vals (packed, the layout of `dout`)
+    double* hout = nullptr;
+    double* dx = nullptr;       // device: x (padded row)
+    double* dout = nullptr;     // device: f(2) | grad(ldz_e) | g(ldg_e) | vals(ldv_e)
+    int64_t o_grad = 0, o_g = 0, o_vals = 0, total = 0;
+    bool valid = false;         // hout holds the results for the x stored in hx
+};
+
+struct Registration {
+    double* ptr;
+    int64_t ld, rows;
 };
 
 }  // namespace
@@ -66,6 +100,11 @@ struct qlnlp_handle_s {
     std::vector<QlSeg> segs;
     std::vector<int> seg_begin;
 
+    // multi-device parent: one complete handle per device; the parent itself only answers the integer queries
+    std::vector<qlnlp_handle_s*> subs;
+    std::vector<std::unique_ptr<qlhost::Worker>> drivers;
+    int part = 0, nparts = 1;          // this handle's share of the host cores (multi-device handles split them)
+
     // device state, created at the first evaluation
     bool dev_ready = false;
     double* d_cost = nullptr;
@@ -75,17 +114,28 @@ struct qlnlp_handle_s {
     long long* d_dense_lin = nullptr;  // DENSE mode: linear index of every SPARSE_BLOCK value
     double* d_dense = nullptr;         // DENSE mode: m x n grid
     int sm_count = 0;
-    int blocks_per_sm[3] = {0, 0, 0};  // [JM_NONE, JM_BLOCK, JM_TRUE]
-    size_t smem[3] = {0, 0, 0};
+    int blocks_per_sm[NJM] = {0, 0, 0, 0};
+    size_t smem[NJM] = {0, 0, 0, 0};
     double rmb = 0, rmf = 0, rIb = 0;  // reciprocals of the divisors
     bool fastdiv = false;              // reciprocal-FMA division verified exact for this model
     int64_t last_launch[5] = {0, 0, 0, 0, 0};
-    HostLane lanes[2];
+    HostLane lanes[MAX_LANES];
+    OneEval one;
     std::map<cudaStream_t, unsigned*> tickets;   // work counters, one pair per stream the handle has launched on
     unsigned* ticket_pool = nullptr;             // pre-zeroed counters (128 B apart) so that a launch needs no
     int ticket_pool_used = 0;                    // allocation: launches stay legal inside CUDA-graph capture
-    std::vector<int32_t> true2block;   // position of every SPARSE_TRUE value inside a SPARSE_BLOCK row
-    int64_t ldz_e = 0, ldgrad_e = 0, ldg_e = 0, ldjac_e = 0;   // even leading dimensions of the scratch
+    std::string pci_bus_id;
+
+    // host-pointer path: row plan of the handle's batch pattern, worker pool, registered output buffers
+    std::unique_ptr<qlhost::RowPlan> plan;
+    std::unique_ptr<qlhost::Pool> pool;
+    std::vector<Registration> regs;
+    int64_t opt_host_chunk = 256;
+    int64_t opt_host_threads = 0;      // 0: this handle's share of the process's CPUs
+    int64_t opt_pin_threads = 1;
+    int64_t opt_x_cache = 1;
+    int64_t ldz_e = 0, ldgrad_e = 0, ldg_e = 0, ldjac_e = 0, ldv_e = 0;   // even leading dimensions of the scratch
+    int64_t stat_host_rows = 0, stat_host_lines = 0;                     // rows / 64-byte lines the row builder wrote
 };
 
 namespace {
@@ -125,8 +175,7 @@ void plan_segments(const QlClass& c, std::vector<QlSeg>& segs, std::vector<int>&
     seg_begin.assign(1, 0);
     for (int p = 0; p < c.npass; ++p) {
         const int ka = p * QL_LANES + 1, kb = std::min(c.N, ka + QL_LANES - 1);
-        int idx = 0;
-        for (int k = ka; k <= kb; k += 2, ++idx) {
+        for (int k = ka; k <= kb; k += 2) {
             QlSeg s;
             std::memset(&s, 0, sizeof s);
             const int nk = (k + 1 <= kb) ? 2 : 1;
@@ -148,7 +197,7 @@ void plan_segments(const QlClass& c, std::vector<QlSeg>& segs, std::vector<int>&
             auto it = ids.find(sig);
             if (it == ids.end()) it = ids.emplace(sig, (int)ids.size()).first;
             s.tmpl = (short)it->second;
-            s.buf = (signed char)(segs.size() & 1);      // alternate over the whole evaluation
+            s.buf = 0;      // unused: the kernel alternates the staging buffers with a running counter (ql_seg_buffer)
             segs.push_back(s);
         }
         seg_begin.push_back((int)segs.size());
@@ -183,12 +232,15 @@ const void* kernel_fn(int jm, bool fast, bool ragged)
 {
     if (jm == ql::JM_BLOCK) return kernel_fn_jm<ql::JM_BLOCK>(fast, ragged);
     if (jm == ql::JM_TRUE) return kernel_fn_jm<ql::JM_TRUE>(fast, ragged);
+    if (jm == ql::JM_VALS)      // host-pointer path only: never ragged
+        return fast ? (const void*)ql::eval_kernel<ql::JM_VALS, true, false> : (const void*)ql::eval_kernel<ql::JM_VALS, false, false>;
     return kernel_fn_jm<ql::JM_NONE>(fast, ragged);
 }
 
 // the sparse pattern batched evaluations of this handle produce (DENSE handles batch in SPARSE_BLOCK)
-int batch_jm(qlnlp_handle h);
-int batch_nnz(qlnlp_handle h);
+int batch_jm(const qlnlp_handle_s* h) { return h->jac_mode == QLNLP_JAC_SPARSE_TRUE ? ql::JM_TRUE : ql::JM_BLOCK; }
+int batch_nnz(const qlnlp_handle_s* h) { return h->jac_mode == QLNLP_JAC_SPARSE_TRUE ? h->cls.nnz_true : h->cls.nnz; }
+int jm_nnz(const QlClass& c, int jm) { return jm == ql::JM_TRUE ? c.nnz_true : jm == ql::JM_VALS ? c.nnz_vals : c.nnz; }
 
 // SPARSE_TRUE structure (1-based, value order): like sparse_block_structure restricted to structural non-zeros
 void sparse_true_structure(const QlClass& c, int64_t* rows, int64_t* cols)
@@ -221,18 +273,138 @@ void sparse_true_structure(const QlClass& c, int64_t* rows, int64_t* cols)
     }
 }
 
+// ---- what a host-side row is made of ----------------------------------------------------------------------
+// Position of every SPARSE_TRUE value inside a SPARSE_BLOCK row (both column-major sorted; TRUE is a sub-sequence).
+std::vector<int32_t> true_to_block(const QlClass& c)
+{
+    std::vector<int64_t> rb(c.nnz), cb(c.nnz), rt(c.nnz_true), ct(c.nnz_true);
+    sparse_block_structure(c, rb.data(), cb.data());
+    sparse_true_structure(c, rt.data(), ct.data());
+    std::vector<int32_t> map(c.nnz_true);
+    int64_t j = 0;
+    for (int64_t i = 0; i < c.nnz_true; ++i) {
+        while (rb[j] != rt[i] || cb[j] != ct[i]) ++j;
+        map[i] = (int32_t)j;
+    }
+    return map;
+}
+
+struct ModePattern { int nvar; const unsigned char *vi, *vj; int ncon; const unsigned char *ci, *cj; const double* cv; };
+ModePattern mode_pattern(int mode)
+{
+    if (mode == 1) return {QL_NJ_MODE1, QL_PAT_I_MODE1, QL_PAT_J_MODE1, QL_NJC_MODE1, QL_CPAT_I_MODE1, QL_CPAT_J_MODE1, QL_CPAT_V_MODE1};
+    if (mode == 2) return {QL_NJ_MODE2, QL_PAT_I_MODE2, QL_PAT_J_MODE2, QL_NJC_MODE2, QL_CPAT_I_MODE2, QL_CPAT_J_MODE2, QL_CPAT_V_MODE2};
+    return {QL_NJ_MODE3, QL_PAT_I_MODE3, QL_PAT_J_MODE3, QL_NJC_MODE3, QL_CPAT_I_MODE3, QL_CPAT_J_MODE3, QL_CPAT_V_MODE3};
+}
+// rows the jump Jacobian keeps (planar_quadruped.jl:262-263)
+const int JUMP_KEEP[QL_NX] = {1, 1, 1, 1, 0, 1, 0, 1, 1, 1, 0, 0, 0, 0, 0};
+
+// The constant image of a SPARSE_BLOCK row (everything jac_c! assigns that does not depend on Z; 0 elsewhere) and
+// the position of every VALS element inside the row, in VALS order (layout.h: ql_vals_run_off; the kernel's writer
+// is ql_vals_write_run in true_run.h).
+void block_image_and_vals_map(const QlClass& c, std::vector<double>& image, std::vector<int32_t>& vals_pos)
+{
+    image.assign((size_t)c.nnz, 0.0);
+    vals_pos.clear();
+    vals_pos.reserve((size_t)c.nnz_vals);
+    for (int k = 1; k <= c.N; ++k) {
+        const int base = ql_run_off(c, k);
+        ql_write_run_constants(c, k, image.data() + base);
+        const int theta = base + ql_theta_pos(c, k);
+        if (k == c.N) { vals_pos.push_back(theta); continue; }
+        const bool jump = (k == c.k_trans - 1);
+        const ModePattern mp = mode_pattern(k >= c.k_trans ? 3 : c.init_mode);
+        for (int e = 0; e < mp.ncon; ++e)
+            image[(size_t)(base + ql_rk4_pos(c, k, mp.ci[e], mp.cj[e]))] = (jump && !JUMP_KEEP[mp.ci[e]]) ? 0.0 : mp.cv[e];
+        bool theta_done = false;
+        for (int e = 0; e < mp.nvar; ++e) {
+            if (jump && !JUMP_KEEP[mp.vi[e]]) continue;          // constant zero at the jump knot: stays in the image
+            if (mp.vj[e] >= 3 && !theta_done) { vals_pos.push_back(theta); theta_done = true; }
+            vals_pos.push_back(base + ql_rk4_pos(c, k, mp.vi[e], mp.vj[e]));
+        }
+        if (!theta_done) vals_pos.push_back(theta);
+    }
+}
+
+// Row plan of the handle's batch pattern (SPARSE_BLOCK, or SPARSE_TRUE as a sub-sequence of it).
+int ensure_plan(qlnlp_handle h)
+{
+    if (h->plan) return QLNLP_OK;
+    const QlClass& c = h->cls;
+    std::vector<double> image;
+    std::vector<int32_t> pos;
+    block_image_and_vals_map(c, image, pos);
+    if ((int)pos.size() != c.nnz_vals) return fail(QLNLP_ECUDA, "internal: VALS map has %zu entries, layout says %d", pos.size(), c.nnz_vals);
+    for (size_t i = 1; i < pos.size(); ++i)
+        if (pos[i] <= pos[i - 1]) return fail(QLNLP_ECUDA, "internal: VALS map is not ascending at %zu", i);
+    if (batch_jm(h) == ql::JM_TRUE) {
+        const std::vector<int32_t> t2b = true_to_block(c);
+        std::vector<int32_t> b2t((size_t)c.nnz, -1);
+        for (size_t t = 0; t < t2b.size(); ++t) b2t[(size_t)t2b[t]] = (int32_t)t;
+        std::vector<double> timage(t2b.size());
+        for (size_t t = 0; t < t2b.size(); ++t) timage[t] = image[(size_t)t2b[t]];
+        for (auto& p : pos) {
+            if (b2t[(size_t)p] < 0) return fail(QLNLP_ECUDA, "internal: value-dependent entry outside SPARSE_TRUE");
+            p = b2t[(size_t)p];
+        }
+        image.swap(timage);
+    }
+    h->plan.reset(new (std::nothrow) qlhost::RowPlan((int64_t)image.size(), image.data(), (int64_t)pos.size(), pos.data()));
+    if (!h->plan) return fail(QLNLP_ENOMEM, "out of host memory");
+    return QLNLP_OK;
+}
+
+int env_int(const char* name, int dflt)
+{
+    if (const char* e = std::getenv(name)) {
+        const int n = std::atoi(e);
+        if (n > 0) return n;
+    }
+    return dflt;
+}
+
+// The worker pool of this handle: its share of the CPUs the process may use.  With one process per GPU (torchrun)
+// the ranks of a node split the cores (LOCAL_RANK of LOCAL_WORLD_SIZE); a multi-device handle splits its share
+// again between its devices; on a multi-socket host the share is taken from the CPUs next to the GPU.
+int ensure_pool(qlnlp_handle h)
+{
+    if (h->pool) return QLNLP_OK;
+    const int lws = env_int("LOCAL_WORLD_SIZE", 1);
+    const int lr = std::getenv("LOCAL_RANK") ? std::atoi(std::getenv("LOCAL_RANK")) : 0;
+    const std::vector<int> all = qlhost::affinity_cpus();
+    std::vector<int> near = qlhost::cpus_near_pci_device(h->pci_bus_id.c_str());
+    const int nparts = lws * h->nparts, part = lr * h->nparts + h->part;
+    std::vector<int> mine;
+    if (near.size() == all.size() || near.empty()) {
+        mine = qlhost::cpu_slice(all, part, nparts);
+    } else {
+        // several CPU groups (sockets): the parts are spread evenly over them
+        const int groups = std::max<int>(1, (int)((all.size() + near.size() / 2) / near.size()));
+        const int per_group = (nparts + groups - 1) / groups;
+        mine = qlhost::cpu_slice(near, part % per_group, per_group);
+    }
+    int T = (int)mine.size();
+    if (h->opt_host_threads > 0) T = (int)h->opt_host_threads;
+    T = env_int("QLNLP_HOST_THREADS", T);
+    T = std::max(1, std::min(T, 256));
+    const bool pin = h->opt_pin_threads != 0 && env_int("QLNLP_PIN_THREADS", 1) != 0 && !std::getenv("QLNLP_NO_PIN");
+    h->pool.reset(new (std::nothrow) qlhost::Pool(T, mine, pin));
+    if (!h->pool) return fail(QLNLP_ENOMEM, "out of host memory");
+    return QLNLP_OK;
+}
+
 int check_handle(qlnlp_handle h)
 {
     if (!h) return fail(QLNLP_EINVAL, "null handle");
     return QLNLP_OK;
 }
+// the handle that owns device state: a multi-device parent forwards single-device work to its first device
+qlnlp_handle first(qlnlp_handle h) { return h->subs.empty() ? h : h->subs[0]; }
 
+// Binds the handle to its device (first call: tables, occupancy, streams).  The caller holds a DeviceGuard.
 int ensure_device(qlnlp_handle h)
 {
-    if (h->dev_ready) {
-        CUDA_TRY(cudaSetDevice(h->device));
-        return QLNLP_OK;
-    }
+    if (h->dev_ready) return QLNLP_OK;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -246,6 +418,8 @@ int ensure_device(qlnlp_handle h)
         return fail(QLNLP_ENODEVICE, "device %d is sm_%d%d; this build targets sm_100a (B200) only", h->device, prop.major,
                     prop.minor);
     h->sm_count = prop.multiProcessorCount;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, h->device) == cudaSuccess) h->pci_bus_id = bus;
 
     CUDA_TRY(cudaMalloc(&h->d_cost, h->cost.size() * sizeof(double)));
     CUDA_TRY(cudaMemcpy(h->d_cost, h->cost.data(), h->cost.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -257,33 +431,41 @@ int ensure_device(qlnlp_handle h)
     CUDA_TRY(cudaMalloc(&h->d_seg_begin, h->seg_begin.size() * sizeof(int)));
     CUDA_TRY(cudaMemcpy(h->d_seg_begin, h->seg_begin.data(), h->seg_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
 
-    for (int wj = 0; wj < 3; ++wj) {
+    for (int wj = 0; wj < NJM; ++wj) {
         h->smem[wj] = ql::smem_bytes(h->cls.N, wj);
         if (h->smem[wj] > (size_t)prop.sharedMemPerBlockOptin)
             return fail(QLNLP_EINVAL, "N=%d needs %zu B of shared memory per warp (> %zu)", h->cls.N, h->smem[wj],
                         (size_t)prop.sharedMemPerBlockOptin);
-      for (int rg = 0; rg < 2; ++rg) {
-        const void* fn = kernel_fn(wj, h->fastdiv, rg != 0);
-        // the attribute is per FUNCTION, shared by every handle of the process: always raise it to the device
-        // limit, never to this handle's own (possibly smaller) requirement
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, h->smem[wj]));
-        if (nb < 1) return fail(QLNLP_ECUDA, "kernel does not fit on an SM");
-        if (const char* e = std::getenv("QLNLP_BLOCKS_PER_SM")) {       // tuning knob: fewer resident warps per SM
-            const int cap = std::atoi(e);
-            if (cap >= 1 && cap < nb) nb = cap;
+        for (int rg = 0; rg < 2; ++rg) {
+            if (rg && wj == ql::JM_VALS) continue;
+            const void* fn = kernel_fn(wj, h->fastdiv, rg != 0);
+            // the attribute is per FUNCTION, shared by every handle of the process: always raise it to the device
+            // limit, never to this handle's own (possibly smaller) requirement
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            int nb = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, h->smem[wj]));
+            if (nb < 1) return fail(QLNLP_ECUDA, "kernel does not fit on an SM");
+            if (const char* env = std::getenv("QLNLP_BLOCKS_PER_SM")) {       // tuning knob: fewer resident warps per SM
+                const int cap = std::atoi(env);
+                if (cap >= 1 && cap < nb) nb = cap;
+            }
+            h->blocks_per_sm[wj] = rg ? std::min(h->blocks_per_sm[wj], nb) : nb;
         }
-        h->blocks_per_sm[wj] = rg ? std::min(h->blocks_per_sm[wj], nb) : nb;
-      }
     }
     for (auto& ln : h->lanes) {
         CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
     }
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->one.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&h->ticket_pool, 128 * TICKET_POOL));
     CUDA_TRY(cudaMemset(h->ticket_pool, 0, 128 * TICKET_POOL));
+    const QlClass& c = h->cls;
+    h->ldz_e = (c.n_nlp + 1) & ~1;
+    h->ldgrad_e = h->ldz_e;
+    h->ldg_e = (c.m_nlp + 1) & ~1;
+    h->ldjac_e = (batch_nnz(h) + 1) & ~1;
+    h->ldv_e = (c.nnz_vals + 1) & ~1;
     // the set-up copies above ran on the legacy default stream and may still be in flight when cudaMemcpy returns
     // (pageable source); launches go to arbitrary, possibly non-blocking streams, so finish the set-up first
     CUDA_TRY(cudaDeviceSynchronize());
@@ -296,20 +478,20 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
 {
     const QlClass& c = h->cls;
     if (B < 0) return fail(QLNLP_EINVAL, "negative batch");
+    if (B == 0) return QLNLP_OK;          // an empty shard is not an error (its pointers may be NULL)
     if (!io || !io->Z) return fail(QLNLP_EINVAL, "io->Z is required");
     if (rg) {
         if (!rg->z_off || (io->g && !rg->g_off) || (io->jac && !rg->jac_off))
             return fail(QLNLP_EINVAL, "ragged launch: offset tables are required for every requested array");
     } else {
-    if (io->ldz < c.n_nlp) return fail(QLNLP_EINVAL, "ldz %lld < n_nlp %d", (long long)io->ldz, c.n_nlp);
-    if (io->grad && io->ldgrad < c.n_nlp) return fail(QLNLP_EINVAL, "ldgrad %lld < n_nlp %d", (long long)io->ldgrad, c.n_nlp);
-    if (io->g && io->ldg < c.m_nlp) return fail(QLNLP_EINVAL, "ldg %lld < m_nlp %d", (long long)io->ldg, c.m_nlp);
+        if (io->ldz < c.n_nlp) return fail(QLNLP_EINVAL, "ldz %lld < n_nlp %d", (long long)io->ldz, c.n_nlp);
+        if (io->grad && io->ldgrad < c.n_nlp) return fail(QLNLP_EINVAL, "ldgrad %lld < n_nlp %d", (long long)io->ldgrad, c.n_nlp);
+        if (io->g && io->ldg < c.m_nlp) return fail(QLNLP_EINVAL, "ldg %lld < m_nlp %d", (long long)io->ldg, c.m_nlp);
     }
     const int jm_jac = jm_force >= 0 ? jm_force : batch_jm(h);
-    const int nnz_jac = jm_jac == ql::JM_TRUE ? c.nnz_true : c.nnz;
+    const int nnz_jac = jm_nnz(c, jm_jac);
     if (!rg && io->jac && io->ldjac < nnz_jac) return fail(QLNLP_EINVAL, "ldjac %lld < nnz %d", (long long)io->ldjac, nnz_jac);
     if ((reinterpret_cast<uintptr_t>(io->Z) & 7) != 0) return fail(QLNLP_EINVAL, "Z must be 8-byte aligned");
-    if (B == 0) return QLNLP_OK;
 
     ql::Launch P;
     P.c = c;
@@ -352,15 +534,22 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     // re-arms it).  Concurrent launches of the handle on different streams get different counters.
     auto it = h->tickets.find(stream);
     if (it == h->tickets.end()) {
-        unsigned* d = nullptr;
-        if (h->ticket_pool_used < TICKET_POOL) {
-            d = h->ticket_pool + 32 * h->ticket_pool_used++;      // zeroed (and synchronised) at set-up
-        } else {
-            CUDA_TRY(cudaMalloc(&d, 128));
-            // zero it ON THIS STREAM: cudaMemset on device memory is asynchronous (legacy default stream) and would
-            // not be ordered before a launch on a non-blocking stream
-            CUDA_TRY(cudaMemsetAsync(d, 0, 128, stream));
+        if (h->ticket_pool_used >= TICKET_POOL) {
+            // Every counter of the pre-zeroed pool belongs to a stream.  Streams come and go (torch pools), so wait
+            // for the handle's outstanding launches and start the pool over rather than allocating (an allocation
+            // here would make the launch illegal inside a CUDA-graph capture, and a faulted kernel could leave a
+            // counter un-re-armed: the reset also heals that).
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(stream, &cap);
+            if (cap != cudaStreamCaptureStatusNone)
+                return fail(QLNLP_EINVAL, "more than %d streams used with this handle: cannot recycle work counters during a graph capture", TICKET_POOL);
+            CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemset(h->ticket_pool, 0, 128 * TICKET_POOL));
+            CUDA_TRY(cudaDeviceSynchronize());
+            h->tickets.clear();
+            h->ticket_pool_used = 0;
         }
+        unsigned* d = h->ticket_pool + 32 * h->ticket_pool_used++;      // zeroed (and synchronised) at set-up
         it = h->tickets.emplace(stream, d).first;
     }
     P.ticket = it->second;
@@ -387,97 +576,16 @@ int reserve_lane(qlnlp_handle h, HostLane& ln, int64_t cap)
 {
     if (ln.cap >= cap) return QLNLP_OK;
     free_lane(ln);
-    const QlClass& c = h->cls;
-    h->ldz_e = (c.n_nlp + 1) & ~1;
-    h->ldgrad_e = h->ldz_e;
-    h->ldg_e = (c.m_nlp + 1) & ~1;
-    h->ldjac_e = (batch_nnz(h) + 1) & ~1;
     CUDA_TRY(cudaMalloc(&ln.Z, sizeof(double) * cap * h->ldz_e));
     CUDA_TRY(cudaMalloc(&ln.x0, sizeof(double) * cap * QL_NX));
     CUDA_TRY(cudaMalloc(&ln.xf, sizeof(double) * cap * QL_NX));
     CUDA_TRY(cudaMalloc(&ln.f, sizeof(double) * cap));
     CUDA_TRY(cudaMalloc(&ln.grad, sizeof(double) * cap * h->ldgrad_e));
     CUDA_TRY(cudaMalloc(&ln.g, sizeof(double) * cap * h->ldg_e));
-    CUDA_TRY(cudaMalloc(&ln.jac, sizeof(double) * cap * h->ldjac_e));
-    if (batch_jm(h) == ql::JM_BLOCK)
-        CUDA_TRY(cudaHostAlloc(&ln.stage, sizeof(double) * cap * ((c.nnz_true + 1) & ~1), cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc(&ln.jac, sizeof(double) * cap * std::max(h->ldjac_e, h->ldv_e)));
+    CUDA_TRY(cudaHostAlloc(&ln.stage, sizeof(double) * cap * h->ldv_e, cudaHostAllocDefault));
     ln.cap = cap;
     return QLNLP_OK;
-}
-
-// ---- compact transfer of SPARSE_BLOCK rows to the host -----------------------------------------------------
-// 85 % of a SPARSE_BLOCK row are structural zeros.  For host-pointer batches the device therefore produces the
-// SPARSE_TRUE values (38.7 KB instead of 257 KB per evaluation cross PCIe) and host threads rebuild the rows the
-// caller asked for: zero-fill + scatter through `true2block`.  No arithmetic happens on the host.
-void build_true2block(qlnlp_handle h)
-{
-    const QlClass& c = h->cls;
-    std::vector<int64_t> rb(c.nnz), cb(c.nnz), rt(c.nnz_true), ct(c.nnz_true);
-    sparse_block_structure(c, rb.data(), cb.data());
-    sparse_true_structure(c, rt.data(), ct.data());
-    h->true2block.resize(c.nnz_true);
-    int64_t j = 0;
-    for (int64_t i = 0; i < c.nnz_true; ++i) {          // both lists are column-major sorted; TRUE is a sub-sequence
-        while (rb[j] != rt[i] || cb[j] != ct[i]) ++j;
-        h->true2block[i] = (int32_t)j;
-    }
-}
-
-int host_threads()
-{
-    if (const char* e = std::getenv("QLNLP_HOST_THREADS")) {
-        const int n = std::atoi(e);
-        if (n > 0) return n;
-    }
-    unsigned hw = std::thread::hardware_concurrency();
-    if (!hw) hw = 4;
-    // one process per GPU (torchrun): share the host cores between the ranks of this node
-    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) {
-        const int n = std::atoi(e);
-        if (n > 1) hw = std::max(1u, hw / (unsigned)n);
-    }
-    return (int)std::min<unsigned>(hw, 64);
-}
-
-void expand_rows(const qlnlp_handle h, const double* stage, int64_t ldt, double* dst, int64_t lddst, int64_t rows)
-{
-    const int nnz_t = h->cls.nnz_true, nnz_b = h->cls.nnz;
-    const int32_t* map = h->true2block.data();
-    const int T = (int)std::min<int64_t>(host_threads(), rows);
-    // Rows are produced front to back, a 16-byte pair at a time, merging the (sorted) non-zero positions into
-    // a stream of zeros; on x86-64 the pairs go out as non-temporal stores, so the row is written once and
-    // never read (a memset + scatter would first pull every line into the cache).
-    auto work = [&](int t) {
-        for (int64_t r = t; r < rows; r += T) {
-            double* out = dst + r * lddst;
-            const double* in = stage + r * ldt;
-            int i = 0, pos = 0;
-            if ((reinterpret_cast<uintptr_t>(out) & 15) != 0 && nnz_b > 0) {     // 8-byte aligned row: peel one element
-                out[0] = (i < nnz_t && map[i] == 0) ? in[i++] : 0.0;
-                pos = 1;
-            }
-            for (; pos + 1 < nnz_b; pos += 2) {
-                double a = 0.0, b = 0.0;
-                if (i < nnz_t && map[i] == pos) a = in[i++];
-                if (i < nnz_t && map[i] == pos + 1) b = in[i++];
-#if defined(__x86_64__)
-                _mm_stream_pd(out + pos, _mm_set_pd(b, a));
-#else
-                out[pos] = a; out[pos + 1] = b;
-#endif
-            }
-            if (pos < nnz_b) out[pos] = (i < nnz_t && map[i] == pos) ? in[i++] : 0.0;
-        }
-#if defined(__x86_64__)
-        _mm_sfence();
-#endif
-    };
-    if (T <= 1) { work(0); return; }
-    std::vector<std::thread> pool;
-    pool.reserve(T - 1);
-    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
-    work(0);
-    for (auto& th : pool) th.join();
 }
 
 // rows of `width` doubles: host (ld_h) <-> device (ld_d)
@@ -489,40 +597,44 @@ cudaError_t copy_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src
     return cudaMemcpy2DAsync(dst, sizeof(double) * ld_dst, src, sizeof(double) * ld_src, sizeof(double) * width, rows, kind, s);
 }
 
-constexpr int64_t HOST_CHUNK = 512;   // evaluations per pipeline stage
-constexpr int64_t COMPACT_MIN_B = 64; // below this the rows are copied as they are
+// is [jac, jac + B rows) inside a registered output buffer, on a row boundary, with the registered row stride?
+bool is_registered(const qlnlp_handle_s* h, const double* jac, int64_t ldjac, int64_t B)
+{
+    for (const Registration& r : h->regs) {
+        if (ldjac != r.ld || jac < r.ptr) continue;
+        const int64_t off = jac - r.ptr;
+        if (off % r.ld == 0 && off / r.ld + B <= r.rows) return true;
+    }
+    return false;
+}
 
-int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
+// ---- host-pointer batches ------------------------------------------------------------------------------------
+// Pipeline over up to MAX_LANES streams, `chunk` evaluations per stage: H2D of the decision vectors, one fused launch,
+// D2H of f / grad / g straight into the caller's arrays.  The Jacobian rows cross PCIe as the VALS stream (only the
+// value-dependent entries: 2,794 of the 32,161 SPARSE_BLOCK values at the default instance) into a pinned staging
+// buffer; while the next chunks are in flight the handle's worker pool assembles the caller's rows from the constant
+// image of the pattern and those values (hostrows.cpp) -- every 64-byte line of a row, or, when the caller has
+// registered the output buffer (qlnlp_host_output_register), only the lines that hold a value-dependent entry.
+int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
 {
     const QlClass& c = h->cls;
-    if (!io || !io->Z) return fail(QLNLP_EINVAL, "io->Z is required");
-    if (io->ldz < c.n_nlp) return fail(QLNLP_EINVAL, "ldz < n_nlp");
-    if (io->grad && io->ldgrad < c.n_nlp) return fail(QLNLP_EINVAL, "ldgrad < n_nlp");
-    if (io->g && io->ldg < c.m_nlp) return fail(QLNLP_EINVAL, "ldg < m_nlp");
-    if (io->jac && io->ldjac < batch_nnz(h)) return fail(QLNLP_EINVAL, "ldjac < nnz");
-    if (B <= 0) return B == 0 ? QLNLP_OK : fail(QLNLP_EINVAL, "negative batch");
-    const int64_t chunk = std::min<int64_t>(B, HOST_CHUNK);
-    const int nlanes = (B > chunk) ? 2 : 1;
-    for (int l = 0; l < nlanes; ++l) {
-        int rc = reserve_lane(h, h->lanes[l], chunk);
-        if (rc) return rc;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, env_int("QLNLP_HOST_CHUNK", (int)h->opt_host_chunk)));
+    const int64_t nchunks = (B + chunk - 1) / chunk;
+    const int nlanes = (int)std::min<int64_t>(MAX_LANES, nchunks);
+    for (int l = 0; l < nlanes; ++l)
+        if (int rc = reserve_lane(h, h->lanes[l], chunk)) return rc;
+    const bool compact = io->jac && B >= COMPACT_MIN_B;
+    bool touched_only = false;
+    if (compact) {
+        if (int rc = ensure_plan(h)) return rc;
+        if (int rc = ensure_pool(h)) return rc;
+        touched_only = is_registered(h, io->jac, io->ldjac, B);
     }
-    // SPARSE_BLOCK rows for a host caller: ship the structural non-zeros, rebuild the rows with host threads
-    const bool compact = io->jac && batch_jm(h) == ql::JM_BLOCK && B >= COMPACT_MIN_B;
-    const int64_t ldt = (c.nnz_true + 1) & ~1;
-    if (compact && h->true2block.empty()) build_true2block(h);
+    const int nnz_b = batch_nnz(h);
 
-    struct Pending { HostLane* ln; int64_t b0, nb; } prev = {nullptr, 0, 0};
-    auto finish = [&](const Pending& pd) -> int {
-        if (!pd.ln) return QLNLP_OK;
-        CUDA_TRY(cudaEventSynchronize(pd.ln->done));
-        expand_rows(h, pd.ln->stage, ldt, io->jac + pd.b0 * io->ldjac, io->ldjac, pd.nb);
-        return QLNLP_OK;
-    };
-    int li = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += chunk, li ^= 1) {
-        HostLane& ln = h->lanes[nlanes == 2 ? li : 0];
-        const int64_t nb = std::min(chunk, B - b0);
+    auto enqueue = [&](int64_t i) -> int {
+        HostLane& ln = h->lanes[i % nlanes];
+        const int64_t b0 = i * chunk, nb = std::min(chunk, B - b0);
         cudaStream_t s = ln.stream;
         CUDA_TRY(copy_rows(ln.Z, h->ldz_e, io->Z + b0 * io->ldz, io->ldz, c.n_nlp, nb, cudaMemcpyHostToDevice, s));
         if (io->x0) CUDA_TRY(cudaMemcpyAsync(ln.x0, io->x0 + b0 * QL_NX, sizeof(double) * nb * QL_NX, cudaMemcpyHostToDevice, s));
@@ -535,47 +647,216 @@ int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
         d.f = io->f ? ln.f : nullptr;
         d.grad = io->grad ? ln.grad : nullptr; d.ldgrad = h->ldgrad_e;
         d.g = io->g ? ln.g : nullptr; d.ldg = h->ldg_e;
-        d.jac = io->jac ? ln.jac : nullptr; d.ldjac = compact ? ldt : h->ldjac_e;
-        int rc = launch(h, nb, &d, s, compact ? ql::JM_TRUE : -1);
-        if (rc) return rc;
+        d.jac = io->jac ? ln.jac : nullptr; d.ldjac = compact ? h->ldv_e : h->ldjac_e;
+        if (int rc = launch(h, nb, &d, s, compact ? ql::JM_VALS : -1)) return rc;
         if (io->f) CUDA_TRY(cudaMemcpyAsync(io->f + b0, ln.f, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
         if (io->grad) CUDA_TRY(copy_rows(io->grad + b0 * io->ldgrad, io->ldgrad, ln.grad, h->ldgrad_e, c.n_nlp, nb, cudaMemcpyDeviceToHost, s));
         if (io->g) CUDA_TRY(copy_rows(io->g + b0 * io->ldg, io->ldg, ln.g, h->ldg_e, c.m_nlp, nb, cudaMemcpyDeviceToHost, s));
         if (compact) {
-            CUDA_TRY(cudaMemcpyAsync(ln.stage, ln.jac, sizeof(double) * nb * ldt, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(ln.stage, ln.jac, sizeof(double) * nb * h->ldv_e, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaEventRecord(ln.done, s));
-            if (int rc2 = finish(prev)) return rc2;          // expand the previous chunk while this one is in flight
-            prev = {&ln, b0, nb};
         } else if (io->jac) {
-            CUDA_TRY(copy_rows(io->jac + b0 * io->ldjac, io->ldjac, ln.jac, h->ldjac_e, batch_nnz(h), nb, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(copy_rows(io->jac + b0 * io->ldjac, io->ldjac, ln.jac, h->ldjac_e, nnz_b, nb, cudaMemcpyDeviceToHost, s));
         }
+        return QLNLP_OK;
+    };
+    auto finish = [&](int64_t i) -> int {
+        if (!compact) return QLNLP_OK;
+        HostLane& ln = h->lanes[i % nlanes];
+        const int64_t b0 = i * chunk, nb = std::min(chunk, B - b0);
+        CUDA_TRY(cudaEventSynchronize(ln.done));
+        double* rows = io->jac + b0 * io->ldjac;
+        h->plan->build(h->pool.get(), ln.stage, h->ldv_e, rows, io->ldjac, nb, touched_only);
+        h->stat_host_rows += nb;
+        h->stat_host_lines += nb * (touched_only ? h->plan->touched_lines((int)((reinterpret_cast<uintptr_t>(rows) >> 3) & 7))
+                                                 : (h->plan->nnz() + 7) / 8);
+        return QLNLP_OK;
+    };
+    for (int64_t i = 0; i < nchunks; ++i) {
+        if (i >= nlanes)
+            if (int rc = finish(i - nlanes)) return rc;      // frees the lane chunk i is about to use
+        if (int rc = enqueue(i)) return rc;
     }
-    if (int rc = finish(prev)) return rc;
+    for (int64_t i = std::max<int64_t>(0, nchunks - nlanes); i < nchunks; ++i)
+        if (int rc = finish(i)) return rc;
     for (int l = 0; l < nlanes; ++l) CUDA_TRY(cudaStreamSynchronize(h->lanes[l].stream));
     return QLNLP_OK;
 }
 
-int batch_jm(qlnlp_handle h) { return h->jac_mode == QLNLP_JAC_SPARSE_TRUE ? ql::JM_TRUE : ql::JM_BLOCK; }
-int batch_nnz(qlnlp_handle h) { return h->jac_mode == QLNLP_JAC_SPARSE_TRUE ? h->cls.nnz_true : h->cls.nnz; }
-
-}  // namespace
-
-// =============================================================================== C ABI
-extern "C" {
-
-int qlnlp_version(void) { return QLNLP_VERSION; }
-
-const char* qlnlp_last_error(void) { return g_err.c_str(); }
-
-int qlnlp_create(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_handle* out)
+int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
 {
-    if (!d || !out) return fail(QLNLP_EINVAL, "null argument");
-    *out = nullptr;
-    if (d->N < 2 || d->N > QL_MAX_N) return fail(QLNLP_EINVAL, "N=%lld outside [2, 1024]", (long long)d->N);
-    if (d->k_trans < 1 || d->k_trans > d->N) return fail(QLNLP_EINVAL, "k_trans=%lld outside [1, N]", (long long)d->k_trans);
-    if (d->init_mode != 1 && d->init_mode != 2) return fail(QLNLP_EINVAL, "init_mode must be 1 or 2");
-    if (jac_mode != QLNLP_JAC_SPARSE_BLOCK && jac_mode != QLNLP_JAC_DENSE && jac_mode != QLNLP_JAC_SPARSE_TRUE) return fail(QLNLP_EINVAL, "unknown jac_mode %d", jac_mode);
-    if (!d->Q || !d->R || !d->q || !d->r || !d->c) return fail(QLNLP_EINVAL, "cost tables are required");
+    const QlClass& c = h->cls;
+    if (B == 0) return QLNLP_OK;
+    if (B < 0) return fail(QLNLP_EINVAL, "negative batch");
+    if (!io || !io->Z) return fail(QLNLP_EINVAL, "io->Z is required");
+    if (io->ldz < c.n_nlp) return fail(QLNLP_EINVAL, "ldz < n_nlp");
+    if (io->grad && io->ldgrad < c.n_nlp) return fail(QLNLP_EINVAL, "ldgrad < n_nlp");
+    if (io->g && io->ldg < c.m_nlp) return fail(QLNLP_EINVAL, "ldg < m_nlp");
+    if (io->jac && io->ldjac < batch_nnz(h)) return fail(QLNLP_EINVAL, "ldjac < nnz");
+    if (io->jac && (reinterpret_cast<uintptr_t>(io->jac) & 7) != 0) return fail(QLNLP_EINVAL, "jac must be 8-byte aligned");
+    DeviceGuard guard(h->device);
+    if (int rc = ensure_device(h)) return rc;
+    const int rc = eval_host_impl(h, B, io);
+    if (rc != QLNLP_OK) {
+        // copies into caller-owned host memory (and out of the pinned stage) may still be in flight: finish them
+        // before the caller gets its buffers back
+        const std::string msg = g_err;
+        for (auto& ln : h->lanes)
+            if (ln.stream) cudaStreamSynchronize(ln.stream);
+        cudaGetLastError();
+        g_err = msg;
+    }
+    return rc;
+}
+
+// contiguous, balanced split of range(B): the first B % n shards get one extra (sharding.shard_bounds)
+void shard_bounds(int64_t B, int n, int s, int64_t* lo, int64_t* hi)
+{
+    const int64_t q = B / n, r = B % n;
+    *lo = s * q + std::min<int64_t>(s, r);
+    *hi = *lo + q + (s < r ? 1 : 0);
+}
+
+qlnlp_batch_io shard_io(const QlClass&, const qlnlp_batch_io& io, int64_t lo)
+{
+    qlnlp_batch_io d = io;
+    d.Z = io.Z + lo * io.ldz;
+    if (io.x0) d.x0 = io.x0 + lo * QL_NX;
+    if (io.xf) d.xf = io.xf + lo * QL_NX;
+    if (io.f) d.f = io.f + lo;
+    if (io.grad) d.grad = io.grad + lo * io.ldgrad;
+    if (io.g) d.g = io.g + lo * io.ldg;
+    if (io.jac) d.jac = io.jac + lo * io.ldjac;
+    return d;
+}
+
+// ---- single evaluations -------------------------------------------------------------------------------------
+enum { HAVE_F = 1, HAVE_GRAD = 2, HAVE_G = 4, HAVE_J = 8 };
+
+int reserve_one(qlnlp_handle h)
+{
+    OneEval& o = h->one;
+    if (o.hx) return QLNLP_OK;
+    o.o_grad = 2;
+    o.o_g = o.o_grad + h->ldgrad_e;
+    o.o_vals = o.o_g + h->ldg_e;
+    o.total = o.o_vals + h->ldv_e;
+    CUDA_TRY(cudaHostAlloc(&o.hx, sizeof(double) * (h->ldz_e + o.total), cudaHostAllocDefault));
+    o.hout = o.hx + h->ldz_e;
+    CUDA_TRY(cudaMalloc(&o.dx, sizeof(double) * h->ldz_e));
+    CUDA_TRY(cudaMalloc(&o.dout, sizeof(double) * o.total));
+    o.valid = false;
+    return QLNLP_OK;
+}
+
+// One decision vector on host pointers.  Ipopt asks for f, grad f, g and the Jacobian values of an iterate in four
+// separate callbacks (moi.jl:1-24): the first callback at a new x evaluates EVERYTHING with one launch (f, grad, g and
+// the value-dependent Jacobian entries: one H2D copy, one kernel, one D2H copy of 41 KB) and keeps the results; the
+// other callbacks at the same x (compared bit for bit, 9.7 KB) are served from that cache.  The Jacobian values are
+// assembled in the caller's array from the constant image of the pattern + the cached entries.
+int eval_one(qlnlp_handle hh, const double* x, double* f, double* grad, double* g, double* vals)
+{
+    if (int rc = check_handle(hh)) return rc;
+    if (!x) return fail(QLNLP_EINVAL, "null x");
+    qlnlp_handle h = first(hh);
+    const QlClass& c = h->cls;
+    DeviceGuard guard(h->device);
+    if (int rc = ensure_device(h)) return rc;
+    if (int rc = reserve_one(h)) return rc;
+    OneEval& o = h->one;
+    const bool hit = h->opt_x_cache && o.valid && std::memcmp(o.hx, x, sizeof(double) * c.n_nlp) == 0;
+    if (!hit) {
+        o.valid = false;
+        std::memcpy(o.hx, x, sizeof(double) * c.n_nlp);
+        cudaStream_t s = o.stream;
+        CUDA_TRY(cudaMemcpyAsync(o.dx, o.hx, sizeof(double) * c.n_nlp, cudaMemcpyHostToDevice, s));
+        qlnlp_batch_io d;
+        std::memset(&d, 0, sizeof d);
+        d.Z = o.dx; d.ldz = h->ldz_e;
+        d.f = o.dout;
+        d.grad = o.dout + o.o_grad; d.ldgrad = h->ldgrad_e;
+        d.g = o.dout + o.o_g; d.ldg = h->ldg_e;
+        d.jac = o.dout + o.o_vals; d.ldjac = h->ldv_e;
+        if (int rc = launch(h, 1, &d, s, ql::JM_VALS)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(o.hout, o.dout, sizeof(double) * o.total, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        o.valid = true;
+    }
+    if (f) *f = o.hout[0];
+    if (grad) std::memcpy(grad, o.hout + o.o_grad, sizeof(double) * c.n_nlp);
+    if (g) std::memcpy(g, o.hout + o.o_g, sizeof(double) * c.m_nlp);
+    if (vals) {
+        if (int rc = ensure_plan(h)) return rc;
+        h->plan->build_rows(o.hout + o.o_vals, h->ldv_e, vals, h->plan->nnz(), 0, 1, false);
+    }
+    return QLNLP_OK;
+}
+
+// DENSE: evaluate SPARSE_BLOCK on the device, scatter into the zeroed m x n grid, copy back
+int eval_dense_jacobian(qlnlp_handle hh, const double* x, double* vals)
+{
+    if (!x) return fail(QLNLP_EINVAL, "null x");
+    qlnlp_handle h = first(hh);
+    DeviceGuard guard(h->device);
+    if (int rc = ensure_device(h)) return rc;
+    const QlClass& c = h->cls;
+    const size_t dense_n = (size_t)c.m_nlp * c.n_nlp;
+    if (!h->d_dense_lin) {
+        std::vector<int64_t> rows(c.nnz), cols(c.nnz);
+        sparse_block_structure(c, rows.data(), cols.data());
+        std::vector<long long> lin(c.nnz);
+        for (int i = 0; i < c.nnz; ++i) lin[i] = (rows[i] - 1) + (long long)c.m_nlp * (cols[i] - 1);
+        CUDA_TRY(cudaMalloc(&h->d_dense_lin, sizeof(long long) * c.nnz));
+        CUDA_TRY(cudaMemcpy(h->d_dense_lin, lin.data(), sizeof(long long) * c.nnz, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&h->d_dense, sizeof(double) * dense_n));
+        CUDA_TRY(cudaDeviceSynchronize());     // set-up copy on the default stream before work on the lane's stream
+    }
+    HostLane& ln = h->lanes[0];
+    if (int rc = reserve_lane(h, ln, 1)) return rc;
+    cudaStream_t s = ln.stream;
+    CUDA_TRY(cudaMemcpyAsync(ln.Z, x, sizeof(double) * c.n_nlp, cudaMemcpyHostToDevice, s));
+    qlnlp_batch_io d;
+    std::memset(&d, 0, sizeof d);
+    d.Z = ln.Z; d.ldz = h->ldz_e;
+    d.jac = ln.jac; d.ldjac = h->ldjac_e;
+    int rc = launch(h, 1, &d, s);
+    if (rc == QLNLP_OK) {
+        cudaError_t e = cudaMemsetAsync(h->d_dense, 0, sizeof(double) * dense_n, s);
+        if (e == cudaSuccess) {
+            ql::scatter_dense_kernel<<<(c.nnz + 255) / 256, 256, 0, s>>>(ln.jac, h->d_dense_lin, h->d_dense, c.nnz);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(vals, h->d_dense, sizeof(double) * dense_n, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = fail(QLNLP_ECUDA, "dense Jacobian: %s", cudaGetErrorString(e));
+    }
+    const std::string msg = g_err;
+    const cudaError_t es = cudaStreamSynchronize(s);      // also on the error path: `vals` is caller-owned
+    if (rc == QLNLP_OK && es != cudaSuccess) return fail(QLNLP_ECUDA, "dense Jacobian: %s", cudaGetErrorString(es));
+    g_err = msg;
+    return rc;
+}
+
+void destroy_device_state(qlnlp_handle h)
+{
+    if (!h->dev_ready) return;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();     // launches on caller streams may still use the handle's tables and counters
+    for (auto& ln : h->lanes) {
+        if (ln.stream) cudaStreamSynchronize(ln.stream);
+        free_lane(ln);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+        if (ln.done) cudaEventDestroy(ln.done);
+    }
+    if (h->one.stream) cudaStreamDestroy(h->one.stream);
+    if (h->one.hx) cudaFreeHost(h->one.hx);
+    cudaFree(h->one.dx); cudaFree(h->one.dout);
+    cudaFree(h->ticket_pool);
+    cudaFree(h->d_cost); cudaFree(h->d_x0xf); cudaFree(h->d_segs); cudaFree(h->d_seg_begin);
+    cudaFree(h->d_dense_lin); cudaFree(h->d_dense);
+}
+
+int create_one(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_handle* out)
+{
     qlnlp_handle h = new (std::nothrow) qlnlp_handle_s();
     if (!h) return fail(QLNLP_ENOMEM, "out of host memory");
     ql_class_init(&h->cls, (int)d->N, (int)d->k_trans, (int)d->init_mode, d->model.g, d->model.mb, d->model.mf, d->model.lb);
@@ -608,24 +889,63 @@ int qlnlp_create(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_ha
     return QLNLP_OK;
 }
 
+int check_desc(const qlnlp_problem_desc* d, int jac_mode)
+{
+    if (d->N < 2 || d->N > QL_MAX_N) return fail(QLNLP_EINVAL, "N=%lld outside [2, 1024]", (long long)d->N);
+    if (d->k_trans < 1 || d->k_trans > d->N) return fail(QLNLP_EINVAL, "k_trans=%lld outside [1, N]", (long long)d->k_trans);
+    if (d->init_mode != 1 && d->init_mode != 2) return fail(QLNLP_EINVAL, "init_mode must be 1 or 2");
+    if (jac_mode != QLNLP_JAC_SPARSE_BLOCK && jac_mode != QLNLP_JAC_DENSE && jac_mode != QLNLP_JAC_SPARSE_TRUE) return fail(QLNLP_EINVAL, "unknown jac_mode %d", jac_mode);
+    if (!d->Q || !d->R || !d->q || !d->r || !d->c) return fail(QLNLP_EINVAL, "cost tables are required");
+    return QLNLP_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int qlnlp_version(void) { return QLNLP_VERSION; }
+
+const char* qlnlp_last_error(void) { return g_err.c_str(); }
+
+int qlnlp_create(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_handle* out)
+{
+    if (!d || !out) return fail(QLNLP_EINVAL, "null argument");
+    *out = nullptr;
+    if (int rc = check_desc(d, jac_mode)) return rc;
+    return create_one(d, device, jac_mode, out);
+}
+
+int qlnlp_create_multi(const qlnlp_problem_desc* d, const int* devices, int ndev, int jac_mode, qlnlp_handle* out)
+{
+    if (!d || !out || !devices) return fail(QLNLP_EINVAL, "null argument");
+    *out = nullptr;
+    if (ndev < 1 || ndev > 64) return fail(QLNLP_EINVAL, "ndev=%d outside [1, 64]", ndev);
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(QLNLP_EINVAL, "device %d listed twice", devices[i]);
+    if (int rc = check_desc(d, jac_mode)) return rc;
+    qlnlp_handle parent = nullptr;
+    if (int rc = create_one(d, devices[0], jac_mode, &parent)) return rc;
+    for (int i = 0; i < ndev; ++i) {
+        qlnlp_handle sub = nullptr;
+        if (int rc = create_one(d, devices[i], jac_mode, &sub)) { qlnlp_destroy(parent); return rc; }
+        sub->part = i;
+        sub->nparts = ndev;
+        parent->subs.push_back(sub);
+        parent->drivers.emplace_back(new qlhost::Worker());
+    }
+    *out = parent;
+    return QLNLP_OK;
+}
+
 int qlnlp_destroy(qlnlp_handle h)
 {
     if (!h) return QLNLP_OK;
-    if (h->dev_ready) {
-        cudaSetDevice(h->device);
-        cudaDeviceSynchronize();     // launches on caller streams may still use the handle's tables and counters
-        for (auto& ln : h->lanes) {
-            if (ln.stream) cudaStreamSynchronize(ln.stream);
-            free_lane(ln);
-            if (ln.stream) cudaStreamDestroy(ln.stream);
-            if (ln.done) cudaEventDestroy(ln.done);
-        }
-        for (auto& kv : h->tickets)
-            if (kv.second < h->ticket_pool || kv.second >= h->ticket_pool + 32 * TICKET_POOL) cudaFree(kv.second);
-        cudaFree(h->ticket_pool);
-        cudaFree(h->d_cost); cudaFree(h->d_x0xf); cudaFree(h->d_segs); cudaFree(h->d_seg_begin);
-        cudaFree(h->d_dense_lin); cudaFree(h->d_dense);
-    }
+    for (auto& w : h->drivers) w->wait();
+    h->drivers.clear();
+    for (qlnlp_handle s : h->subs) qlnlp_destroy(s);
+    destroy_device_state(h);
     delete h;
     return QLNLP_OK;
 }
@@ -637,6 +957,23 @@ int qlnlp_dims(qlnlp_handle h, int64_t* n_nlp, int64_t* m_nlp, int64_t* nnz, int
     if (m_nlp) *m_nlp = h->cls.m_nlp;
     if (nnz) *nnz = (h->jac_mode == QLNLP_JAC_DENSE) ? (int64_t)h->cls.m_nlp * h->cls.n_nlp : batch_nnz(h);
     if (nnz_block) *nnz_block = h->cls.nnz;
+    return QLNLP_OK;
+}
+
+int qlnlp_devices(qlnlp_handle h, int* devices, int cap, int* ndev)
+{
+    if (int rc = check_handle(h)) return rc;
+    const int n = h->subs.empty() ? 1 : (int)h->subs.size();
+    if (ndev) *ndev = n;
+    if (devices)
+        for (int i = 0; i < n && i < cap; ++i) devices[i] = h->subs.empty() ? h->device : h->subs[i]->device;
+    return QLNLP_OK;
+}
+
+int qlnlp_shard_bounds(int64_t B, int nshards, int shard, int64_t* lo, int64_t* hi)
+{
+    if (B < 0 || nshards < 1 || shard < 0 || shard >= nshards || !lo || !hi) return fail(QLNLP_EINVAL, "bad shard arguments");
+    shard_bounds(B, nshards, shard, lo, hi);
     return QLNLP_OK;
 }
 
@@ -686,17 +1023,70 @@ int qlnlp_variable_bounds(qlnlp_handle h, double* xl, double* xu)
     return QLNLP_OK;
 }
 
+int qlnlp_set_option(qlnlp_handle h, const char* name, int64_t value)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!name) return fail(QLNLP_EINVAL, "null option name");
+    auto apply = [&](qlnlp_handle t) -> int {
+        const std::string n(name);
+        if (n == "host_chunk") { if (value < 1) return fail(QLNLP_EINVAL, "host_chunk must be >= 1"); t->opt_host_chunk = value; }
+        else if (n == "host_threads") { if (value < 0) return fail(QLNLP_EINVAL, "host_threads must be >= 0"); t->opt_host_threads = value; t->pool.reset(); }
+        else if (n == "pin_threads") { t->opt_pin_threads = value != 0; t->pool.reset(); }
+        else if (n == "x_cache") { t->opt_x_cache = value != 0; t->one.valid = false; }
+        else return fail(QLNLP_EINVAL, "unknown option '%s'", name);
+        return QLNLP_OK;
+    };
+    if (int rc = apply(h)) return rc;
+    for (qlnlp_handle s : h->subs)
+        if (int rc = apply(s)) return rc;
+    return QLNLP_OK;
+}
+
 int qlnlp_eval_batch_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, void* stream)
 {
     if (int rc = check_handle(h)) return rc;
+    if (!h->subs.empty()) return fail(QLNLP_EINVAL, "multi-device handle: use qlnlp_eval_batch_device_multi");
+    if (B == 0) return QLNLP_OK;
+    DeviceGuard guard(h->device);
     if (int rc = ensure_device(h)) return rc;
     return launch(h, B, io, static_cast<cudaStream_t>(stream));
+}
+
+int qlnlp_eval_batch_device_multi(qlnlp_handle h, const int64_t* B, const qlnlp_batch_io* io, void* const* streams)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!B || !io) return fail(QLNLP_EINVAL, "null argument");
+    const int n = h->subs.empty() ? 1 : (int)h->subs.size();
+    for (int i = 0; i < n; ++i) {
+        qlnlp_handle s = h->subs.empty() ? h : h->subs[i];
+        if (B[i] == 0) continue;
+        DeviceGuard guard(s->device);
+        if (int rc = ensure_device(s)) return rc;
+        if (int rc = launch(s, B[i], io + i, streams ? static_cast<cudaStream_t>(streams[i]) : nullptr)) return rc;
+    }
+    return QLNLP_OK;
+}
+
+int qlnlp_synchronize(qlnlp_handle h)
+{
+    if (int rc = check_handle(h)) return rc;
+    const int n = h->subs.empty() ? 1 : (int)h->subs.size();
+    for (int i = 0; i < n; ++i) {
+        qlnlp_handle s = h->subs.empty() ? h : h->subs[i];
+        if (!s->dev_ready) continue;
+        DeviceGuard guard(s->device);
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    return QLNLP_OK;
 }
 
 int qlnlp_eval_ragged_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, const qlnlp_ragged_io* rg, void* stream)
 {
     if (int rc = check_handle(h)) return rc;
+    if (!h->subs.empty()) return fail(QLNLP_EINVAL, "multi-device handle: ragged launches take a single-device handle");
     if (!rg) return fail(QLNLP_EINVAL, "null ragged descriptor");
+    if (B == 0) return QLNLP_OK;
+    DeviceGuard guard(h->device);
     if (int rc = ensure_device(h)) return rc;
     return launch(h, B, io, static_cast<cudaStream_t>(stream), -1, rg);
 }
@@ -704,23 +1094,88 @@ int qlnlp_eval_ragged_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io
 int qlnlp_eval_batch_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
 {
     if (int rc = check_handle(h)) return rc;
-    if (int rc = ensure_device(h)) return rc;
-    return eval_host(h, B, io);
+    if (h->subs.empty()) return eval_host(h, B, io);
+    if (B == 0) return QLNLP_OK;
+    if (B < 0 || !io) return fail(QLNLP_EINVAL, "bad batch");
+    // contiguous shards, one driver thread per device, no exchange between the devices
+    const int n = (int)h->subs.size();
+    std::vector<int> rcs(n, QLNLP_OK);
+    std::vector<std::string> msgs(n);
+    for (int i = 0; i < n; ++i) {
+        int64_t lo, hi;
+        shard_bounds(B, n, i, &lo, &hi);
+        if (hi == lo) continue;
+        const qlnlp_batch_io d = shard_io(h->cls, *io, lo);
+        qlnlp_handle s = h->subs[i];
+        h->drivers[i]->submit([s, d, lo, hi, i, &rcs, &msgs] {
+            rcs[i] = eval_host(s, hi - lo, &d);
+            if (rcs[i]) msgs[i] = g_err;        // g_err is per thread
+        });
+    }
+    for (auto& w : h->drivers) w->wait();
+    for (int i = 0; i < n; ++i)
+        if (rcs[i]) return fail(rcs[i], "device %d: %s", h->subs[i]->device, msgs[i].c_str());
+    return QLNLP_OK;
 }
 
-static int eval_one(qlnlp_handle h, const double* x, double* f, double* grad, double* g, double* jac)
+int qlnlp_host_output_register(qlnlp_handle h, double* jac, int64_t ldjac, int64_t B)
 {
     if (int rc = check_handle(h)) return rc;
-    if (!x) return fail(QLNLP_EINVAL, "null x");
-    if (int rc = ensure_device(h)) return rc;
-    qlnlp_batch_io io;
-    std::memset(&io, 0, sizeof io);
-    io.Z = x; io.ldz = h->cls.n_nlp;
-    io.f = f;
-    io.grad = grad; io.ldgrad = h->cls.n_nlp;
-    io.g = g; io.ldg = h->cls.m_nlp;
-    io.jac = jac; io.ldjac = batch_nnz(h);
-    return eval_host(h, 1, &io);
+    if (!jac || B < 1) return fail(QLNLP_EINVAL, "bad buffer");
+    if ((reinterpret_cast<uintptr_t>(jac) & 7) != 0) return fail(QLNLP_EINVAL, "jac must be 8-byte aligned");
+    if (ldjac < batch_nnz(h)) return fail(QLNLP_EINVAL, "ldjac < nnz");
+    const int n = h->subs.empty() ? 1 : (int)h->subs.size();
+    // every device's handle may be asked for any slice of the buffer: all of them learn the registration; the
+    // constant image is written once, by the first handle's pool
+    for (int i = 0; i < n; ++i) {
+        qlnlp_handle s = h->subs.empty() ? h : h->subs[i];
+        if (int rc = ensure_plan(s)) return rc;
+        for (auto it = s->regs.begin(); it != s->regs.end();)
+            it = (it->ptr == jac) ? s->regs.erase(it) : it + 1;
+        s->regs.push_back({jac, ldjac, B});
+    }
+    qlnlp_handle s0 = first(h);
+    if (int rc = ensure_pool(s0)) return rc;
+    s0->plan->build(s0->pool.get(), nullptr, 0, jac, ldjac, B, false);
+    return QLNLP_OK;
+}
+
+int qlnlp_host_output_unregister(qlnlp_handle h, double* jac)
+{
+    if (int rc = check_handle(h)) return rc;
+    const int n = h->subs.empty() ? 1 : (int)h->subs.size();
+    for (int i = 0; i < n; ++i) {
+        qlnlp_handle s = h->subs.empty() ? h : h->subs[i];
+        for (auto it = s->regs.begin(); it != s->regs.end();)
+            it = (it->ptr == jac) ? s->regs.erase(it) : it + 1;
+    }
+    return QLNLP_OK;
+}
+
+int qlnlp_host_pin(void* ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return fail(QLNLP_EINVAL, "bad buffer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(QLNLP_ENODEVICE, "no CUDA device available");
+    CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return QLNLP_OK;
+}
+
+int qlnlp_host_unpin(void* ptr)
+{
+    if (!ptr) return fail(QLNLP_EINVAL, "bad buffer");
+    CUDA_TRY(cudaHostUnregister(ptr));
+    return QLNLP_OK;
+}
+
+int qlnlp_eval_all(qlnlp_handle h, const double* x, double* f, double* grad, double* g, double* vals)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (vals && h->jac_mode == QLNLP_JAC_DENSE) {
+        if (int rc = eval_one(h, x, f, grad, g, nullptr)) return rc;
+        return eval_dense_jacobian(h, x, vals);
+    }
+    return eval_one(h, x, f, grad, g, vals);
 }
 
 int qlnlp_eval_objective(qlnlp_handle h, const double* x, double* f)
@@ -746,49 +1201,43 @@ int qlnlp_eval_constraint_jacobian(qlnlp_handle h, const double* x, double* vals
     if (int rc = check_handle(h)) return rc;
     if (!vals) return fail(QLNLP_EINVAL, "null output");
     if (h->jac_mode != QLNLP_JAC_DENSE) return eval_one(h, x, nullptr, nullptr, nullptr, vals);
-
-    // DENSE: evaluate SPARSE_BLOCK on the device, scatter into the zeroed m x n grid, copy back
-    if (!x) return fail(QLNLP_EINVAL, "null x");
-    if (int rc = ensure_device(h)) return rc;
-    const QlClass& c = h->cls;
-    const size_t dense_n = (size_t)c.m_nlp * c.n_nlp;
-    if (!h->d_dense_lin) {
-        std::vector<int64_t> rows(c.nnz), cols(c.nnz);
-        sparse_block_structure(c, rows.data(), cols.data());
-        std::vector<long long> lin(c.nnz);
-        for (int i = 0; i < c.nnz; ++i) lin[i] = (rows[i] - 1) + (long long)c.m_nlp * (cols[i] - 1);
-        CUDA_TRY(cudaMalloc(&h->d_dense_lin, sizeof(long long) * c.nnz));
-        CUDA_TRY(cudaMemcpy(h->d_dense_lin, lin.data(), sizeof(long long) * c.nnz, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&h->d_dense, sizeof(double) * dense_n));
-        CUDA_TRY(cudaDeviceSynchronize());     // set-up copy on the default stream before work on the lane's stream
-    }
-    HostLane& ln = h->lanes[0];
-    if (int rc = reserve_lane(h, ln, 1)) return rc;
-    cudaStream_t s = ln.stream;
-    CUDA_TRY(cudaMemcpyAsync(ln.Z, x, sizeof(double) * c.n_nlp, cudaMemcpyHostToDevice, s));
-    qlnlp_batch_io d;
-    std::memset(&d, 0, sizeof d);
-    d.Z = ln.Z; d.ldz = h->ldz_e;
-    d.jac = ln.jac; d.ldjac = h->ldjac_e;
-    if (int rc = launch(h, 1, &d, s)) return rc;
-    CUDA_TRY(cudaMemsetAsync(h->d_dense, 0, sizeof(double) * dense_n, s));
-    ql::scatter_dense_kernel<<<(c.nnz + 255) / 256, 256, 0, s>>>(ln.jac, h->d_dense_lin, h->d_dense, c.nnz);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(vals, h->d_dense, sizeof(double) * dense_n, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    return QLNLP_OK;
+    return eval_dense_jacobian(h, x, vals);
 }
 
 int qlnlp_launch_info(qlnlp_handle h, int64_t info[5])
 {
     if (int rc = check_handle(h)) return rc;
     if (!info) return fail(QLNLP_EINVAL, "null output");
-    for (int i = 0; i < 5; ++i) info[i] = h->last_launch[i];
+    for (int i = 0; i < 5; ++i) info[i] = first(h)->last_launch[i];
     return QLNLP_OK;
 }
 
-/* Test hook (not part of the public header): the segment plan, so CPU tests can check it
- * against the structure without a GPU.  out[i*6 + {0..5}] = k0 nk start end tmpl buf. */
+int qlnlp_host_path_info(qlnlp_handle h, int64_t info[8])
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!info) return fail(QLNLP_EINVAL, "null output");
+    qlnlp_handle s = first(h);
+    if (int rc = ensure_plan(s)) return rc;
+    int64_t rows = 0, lines = 0;
+    const int n = h->subs.empty() ? 1 : (int)h->subs.size();
+    for (int i = 0; i < n; ++i) {
+        const qlnlp_handle t = h->subs.empty() ? h : h->subs[i];
+        rows += t->stat_host_rows;
+        lines += t->stat_host_lines;
+    }
+    info[0] = s->pool ? s->pool->size() : 0;          // worker threads per device (0: pool not started yet)
+    info[1] = s->cls.nnz_vals;                        // doubles per evaluation that cross PCIe for the Jacobian
+    info[2] = s->plan->nnz();                         // doubles per row of the batch pattern
+    info[3] = s->plan->touched_lines(0);              // 64-byte lines rewritten per registered row (aligned row)
+    info[4] = (s->plan->nnz() + 7) / 8;               // 64-byte lines per row
+    info[5] = qlhost::RowPlan::have_avx512() ? 1 : 0;
+    info[6] = rows;                                   // rows assembled so far
+    info[7] = lines;                                  // lines written so far
+    return QLNLP_OK;
+}
+
+/* Test hooks (not part of the public header): let CPU tests check the integer logic without a GPU.
+ * qlnlp_debug_segments: out[i*6 + {0..5}] = k0 nk start end tmpl buf(of the first evaluation). */
 int qlnlp_debug_segments(qlnlp_handle h, int64_t* out, int64_t cap, int64_t* nseg)
 {
     if (int rc = check_handle(h)) return rc;
@@ -797,9 +1246,43 @@ int qlnlp_debug_segments(qlnlp_handle h, int64_t* out, int64_t cap, int64_t* nse
         for (size_t i = 0; i < h->segs.size() && (int64_t)i < cap; ++i) {
             const QlSeg& s = h->segs[i];
             int64_t* o = out + 6 * i;
-            o[0] = s.k0; o[1] = s.nk; o[2] = s.start; o[3] = s.end; o[4] = s.tmpl; o[5] = s.buf;
+            o[0] = s.k0; o[1] = s.nk; o[2] = s.start; o[3] = s.end; o[4] = s.tmpl; o[5] = ql_seg_buffer((unsigned)i);
         }
     }
+    return QLNLP_OK;
+}
+
+/* position of every VALS element inside a row of the handle's batch pattern; returns the count through *n */
+int qlnlp_debug_vals_map(qlnlp_handle h, int32_t* pos, int64_t cap, int64_t* n)
+{
+    if (int rc = check_handle(h)) return rc;
+    const QlClass& c = h->cls;
+    std::vector<double> image;
+    std::vector<int32_t> p;
+    block_image_and_vals_map(c, image, p);
+    if (batch_jm(h) == ql::JM_TRUE) {
+        const std::vector<int32_t> t2b = true_to_block(c);
+        std::vector<int32_t> b2t((size_t)c.nnz, -1);
+        for (size_t t = 0; t < t2b.size(); ++t) b2t[(size_t)t2b[t]] = (int32_t)t;
+        for (auto& q : p) q = b2t[(size_t)q];
+    }
+    if (n) *n = (int64_t)p.size();
+    if (pos)
+        for (size_t i = 0; i < p.size() && (int64_t)i < cap; ++i) pos[i] = p[i];
+    return QLNLP_OK;
+}
+
+/* the host row builder alone (no device): rows of the batch pattern from VALS rows; threads <= 0: the handle's pool */
+int qlnlp_debug_build_rows(qlnlp_handle h, const double* vals, int64_t ldv, double* jac, int64_t ldjac, int64_t rows,
+                           int touched_only, int threads)
+{
+    if (int rc = check_handle(h)) return rc;
+    qlnlp_handle s = first(h);
+    if (int rc = ensure_plan(s)) return rc;
+    if (threads == 1) { s->plan->build_rows(vals, ldv, jac, ldjac, 0, rows, touched_only != 0); return QLNLP_OK; }
+    if (threads > 1) { s->opt_host_threads = threads; s->pool.reset(); }
+    if (int rc = ensure_pool(s)) return rc;
+    s->plan->build(s->pool.get(), vals, ldv, jac, ldjac, rows, touched_only != 0);
     return QLNLP_OK;
 }
 

@@ -22,8 +22,8 @@
 // zeros to persist: every lane writes its knot's whole run into a per-pass staging buffer and the pass goes
 // out as one bulk store.
 // All arithmetic is fp64 with explicit round-to-nearest add/mul/div (no FMA contraction) in the
-// reference's operation order, so g, grad and the Jacobian values are bit-identical to the CPU
-// oracle (sin/cos aside); only the cost reduction order (warp tree vs. sequential) differs.
+// reference's operation order, so f, g, grad and the Jacobian values are bit-identical to the CPU
+// oracle (sin/cos aside); the cost is accumulated knot by knot in the reference's sequential order.
 // Divisions by the model constants use q = a*r, q' = fma(fma(-q, b, a), r, q) with r = RN(1/b), which is
 // the correctly rounded quotient (Markstein); the host verifies this per divisor at create time and falls
 // back to IEEE division (template parameter FASTDIV = false) otherwise.
@@ -173,12 +173,15 @@ struct Launch {
 
 // shared memory carve-up: staged Z (same layout as in HBM) | mbarrier | two J staging buffers | segment plan
 __host__ __device__ inline int zbuf_len(int N) { return QL_NZK * N + 2; }     // n_nlp + 1 rounded up to even, + mbarrier
-enum { JM_NONE = 0, JM_BLOCK = 1, JM_TRUE = 2 };     // which Jacobian value stream the kernel produces
+enum { JM_NONE = 0, JM_BLOCK = 1, JM_TRUE = 2, JM_VALS = 3 };     // which Jacobian value stream the kernel produces
+static_assert(QL_VALS_LEN_MODE1 == QL_VALS_LEN_INIT && QL_VALS_LEN_MODE2 == QL_VALS_LEN_INIT &&
+              QL_VALS_LEN_MODE1_JUMP == QL_VALS_LEN_JUMPK && QL_VALS_LEN_MODE2_JUMP == QL_VALS_LEN_JUMPK &&
+              QL_VALS_LEN_MODE3 == QL_VALS_LEN_M3, "layout.h VALS run lengths out of date");
 __host__ __device__ inline size_t smem_jregion_bytes(int N, int jm)
 {
     const int nseg_max = (N + 1) / 2 + (N + QL_LANES - 1) / QL_LANES;
     if (jm == JM_BLOCK) return sizeof(double) * 2 * QL_JBUF + sizeof(QlSeg) * nseg_max;
-    if (jm == JM_TRUE) return sizeof(double) * QL_TRUE_PBUF;
+    if (jm == JM_TRUE || jm == JM_VALS) return sizeof(double) * QL_TRUE_PBUF;
     return 0;
 }
 __host__ __device__ inline size_t smem_bytes(int N, int jm)
@@ -216,6 +219,9 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
     const unsigned zaddr = smem_addr(zbuf);
     const unsigned jaddr = smem_addr(jb);
     int tmpl0 = -1, tmpl1 = -1;        // template currently held by staging buffer 0 / 1
+    unsigned segctr = 0;               // segments this warp has streamed so far: consecutive segments alternate between
+                                       // the two staging buffers ACROSS evaluations too, so the bulk store that may still
+                                       // be reading a buffer (wait_group.read 1) is never the buffer being rewritten
     // cost coefficients: from shared memory ([41][N], copied once per CTA) when the launch has room for it, else
     // from the field-major global table (L2)
     Consts<FASTDIV> K;
@@ -257,6 +263,9 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
         else cp_async_wait_all();
         __syncwarp();
         double fsum = 0.0;
+        // the kernels without the SPARSE_BLOCK stream are latency-bound: take the next ticket now, so that the atomic's
+        // round trip is hidden behind this evaluation (the SPARSE_BLOCK kernel has no register to spare for it)
+        if (JM != JM_BLOCK) nb = take();
         const long long pi = (RAGGED && P.index) ? __ldg(P.index + b) : b;      // problem number (f, x0, xf, offsets)
         double* const grow = P.g ? P.g + (RAGGED ? __ldg(P.g_off + pi) : b * P.ldg) : nullptr;
         double* const gradrow = P.grad ? P.grad + (RAGGED ? __ldg(P.z_off + pi) : b * P.ldgrad) : nullptr;
@@ -271,17 +280,27 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
             const bool jump = has_u && (k == c.k_trans - 1);   // constraints.jl:29 / :190
             double* const zk = zbuf + (k - 1) * QL_NZK;
 
-            // ---- 1. my knot's slice of Z: x_k, u_k, x_{k+1}
-            double xk[QL_NX], uk[QL_NU], xnx[QL_NX];
+            // ---- 1. my knot's slice of Z: x_k, u_k, x_{k+1} = zk[0..34], fetched with 128-bit shared loads (the knot
+            // stride of 160 B makes 64-bit loads 4-way bank conflicted; 16-byte loads halve the wavefronts)
+            double zin[36];
+            {
+                const double2* zk2 = reinterpret_cast<const double2*>(zk);
 #pragma unroll
-            for (int i = 0; i < QL_NX; ++i) xk[i] = act ? zk[i] : 0.0;
-#pragma unroll
-            for (int i = 0; i < QL_NU; ++i) uk[i] = has_u ? zk[QL_NX + i] : 0.0;
-#pragma unroll
-            for (int i = 0; i < QL_NX; ++i) xnx[i] = has_u ? zk[QL_NZK + i] : 0.0;
+                for (int i = 0; i < 18; ++i) {
+                    const bool ld = (i < 8) ? act : has_u;      // knot N reads x_N only (zk[15] is the padding element)
+                    const double2 v = ld ? zk2[i] : make_double2(0.0, 0.0);
+                    zin[2 * i] = v.x;
+                    zin[2 * i + 1] = v.y;
+                }
+                if (!has_u) zin[QL_NX] = 0.0;
+            }
+            const double* const xk = zin;
+            const double* const uk = zin + QL_NX;
+            const double* const xnx = zin + QL_NZK;
             __syncwarp();       // every lane holds its inputs: this pass's slice of zbuf may be overwritten
 
             // ---- 2. cost and gradient (costs.jl:6-34, quadratic_cost.jl:44-52); gradient in place over Z
+            double lane_term = 0.0;
             if (act && (P.f || gradrow)) {
                 const double* ct = P.cost + (k - 1);
                 const int np = P.npad;
@@ -320,7 +339,15 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                 } else {
                     term = __dadd_rn(__dadd_rn(hq, dq), cq[40]);       // termcost
                 }
-                fsum += term;
+                lane_term = term;
+            }
+            if (P.f) {
+                // costs.jl:9-15 accumulates J knot by knot: do the same (every lane computes the same sum)
+#pragma unroll 8
+                for (int s = 0; s < QL_LANES; ++s) {
+                    const double t = __shfl_sync(0xffffffffu, lane_term, s);
+                    if (p * QL_LANES + s < c.N) fsum = __dadd_rn(fsum, t);
+                }
             }
 
             // flush this pass's gradient slice with coalesced stores; the slice is then free for the defects
@@ -329,11 +356,22 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                 __syncwarp();
                 const int e0 = p * QL_LANES * QL_NZK;
                 const int cnt = min(QL_LANES * QL_NZK, c.n_nlp - e0);
-                for (int i = lane; i < cnt; i += QL_LANES) QL_GST(gradrow + e0 + i, slice[i]);
+                if ((reinterpret_cast<uintptr_t>(gradrow) & 15) == 0) {      // e0 is even: 16-byte stores
+                    const double2* s2 = reinterpret_cast<const double2*>(slice);
+                    double2* d2 = reinterpret_cast<double2*>(gradrow + e0);
+                    for (int i = lane; i < (cnt >> 1); i += QL_LANES) QL_GST(d2 + i, s2[i]);
+                    if ((cnt & 1) && lane == 0) QL_GST(gradrow + e0 + cnt - 1, slice[cnt - 1]);
+                } else {
+                    for (int i = lane; i < cnt; i += QL_LANES) QL_GST(gradrow + e0 + i, slice[i]);
+                }
                 __syncwarp();
             }
 
             // ---- 3. constraints (constraints.jl:145-158) and the RK4 Jacobian values
+            // the defects of this pass go to g[c_dyn + 15 (k_first - 1) ...]: stage them at the same parity as their
+            // destination so that the flush can use 16-byte loads and stores
+            double* const ddst = grow ? grow + c.c_dyn + p * QL_LANES * QL_NX : nullptr;
+            const int dpar = (int)((reinterpret_cast<uintptr_t>(ddst) >> 3) & 1);
             double jv[WITH_JAC ? QL_NJ_MAX : 1];
             double jtheta = 0.0;
             if (has_u && (WITH_JAC || grow)) {
@@ -352,7 +390,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                 }
                 if (grow) {   // dynamics defect, constraints.jl:25-36: 15 consecutive rows per knot, staged in my slice
 #pragma unroll
-                    for (int i = 0; i < QL_NX; ++i) slice[lane * QL_NX + i] = __dsub_rn(xn[i], xnx[i]);
+                    for (int i = 0; i < QL_NX; ++i) slice[dpar + lane * QL_NX + i] = __dsub_rn(xn[i], xnx[i]);
                 }
             }
             if (act && (WITH_JAC || grow)) {
@@ -383,30 +421,40 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
             if (grow) {
                 const int k_first = p * QL_LANES + 1;
                 const int ndyn = min(QL_LANES, c.N - k_first) * QL_NX;      // knots of this pass with k < N
-                double* dst = grow + c.c_dyn + (k_first - 1) * QL_NX;
-                for (int i = lane; i < ndyn; i += QL_LANES) QL_GST(dst + i, slice[i]);
+                // image element j <-> ddst[j - dpar]; the pairs (j, j+1) with j even are 16-byte aligned on both sides
+                const int j0 = dpar, j1 = dpar + ndyn;
+                const int a = (j0 + 1) & ~1, e = j1 & ~1;
+                const double2* s2 = reinterpret_cast<const double2*>(slice);
+                double2* d2 = reinterpret_cast<double2*>(ddst - dpar);
+                for (int i = (a >> 1) + lane; i < (e >> 1); i += QL_LANES) QL_GST(d2 + i, s2[i]);
+                if (lane == 0 && a > j0 && ndyn > 0) QL_GST(ddst, slice[j0]);
+                if (lane == 1 && e < j1 && e >= a) QL_GST(ddst + (e - dpar), slice[e]);
                 __syncwarp();
             }
             if (p == c.npass - 1) {
                 // zbuf is dead: prefetch the next decision vector while the Jacobian values stream out
-                nb = take();
+                if (JM == JM_BLOCK) nb = take();
                 if (nb < P.B) stage_z(zrow_of(nb), zaddr, mbar, c.n_nlp, lane, zbulk);
             }
 
             // ---- 5'. SPARSE_TRUE: every lane writes its whole run; the pass leaves as two bulk stores of 16 knots
             // (a half-pass staging buffer keeps the shared memory per warp small enough for 8 warps per SM)
-            if (JM == JM_TRUE) {
+            if (JM == JM_TRUE || JM == JM_VALS) {
+                auto run_off = [&](int kk) { return JM == JM_TRUE ? ql_true_run_off(c, kk) : ql_vals_run_off(c, kk); };
                 for (int half = 0; half < 2; ++half) {
                     const int k_first = p * QL_LANES + 16 * half + 1;
                     if (k_first > c.N) break;
                     const int k_end = min(c.N, k_first + 15) + 1;
-                    const int start = ql_true_run_off(c, k_first);
-                    const int end = (k_end > c.N) ? c.nnz_true : ql_true_run_off(c, k_end);
+                    const int start = run_off(k_first);
+                    const int end = (k_end > c.N) ? (JM == JM_TRUE ? c.nnz_true : c.nnz_vals) : run_off(k_end);
                     const int base = start & ~1;
                     if (P.bulk && lane == 0) bulk_wait_read<0>();     // the previous store has read the buffer
                     __syncwarp();
-                    if (act && (lane >> 4) == half)
-                        ql_true_write_run(c, k, jv, jtheta, jaddr + 8u * (unsigned)(ql_true_run_off(c, k) - base));
+                    if (act && (lane >> 4) == half) {
+                        const unsigned raddr = jaddr + 8u * (unsigned)(run_off(k) - base);
+                        if (JM == JM_TRUE) ql_true_write_run(c, k, jv, jtheta, raddr);
+                        else ql_vals_write_run(c, k, jv, jtheta, raddr);
+                    }
                     if (bulk) {
                         fence_proxy_async();
                         __syncwarp();
@@ -434,7 +482,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                     const int4 rec = *reinterpret_cast<const int4*>(plan + s);
                     const int start = rec.x, end = rec.y;
                     const int k0 = (int)(short)(rec.z & 0xffff), nk = (int)(signed char)((rec.z >> 16) & 0xff);
-                    const int bi = (rec.z >> 24) & 0xff, tm = (int)(short)(rec.w & 0xffff);
+                    const int bi = ql_seg_buffer(segctr++), tm = (int)(short)(rec.w & 0xffff);
                     double* const buf = jb + bi * QL_JBUF;
                     const unsigned baddr = jaddr + (unsigned)bi * (QL_JBUF * 8u);
                     const int base = start & ~1;                 // image[0] <-> stream offset `base`
@@ -495,12 +543,8 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
             }
         }
 
-        // ---- 6. cost: warp-shuffle tree over the per-lane terms (costs.jl:9-15 sums sequentially)
-        if (P.f) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, off);
-            if (lane == 0) P.f[pi] = fsum;
-        }
+        // ---- 6. cost (accumulated in the reference's order above)
+        if (P.f && lane == 0) P.f[pi] = fsum;
     }
     if (WITH_JAC && P.bulk && lane == 0) bulk_wait_all();
     // the last CTA to leave re-arms the counters for the next launch on this stream

@@ -56,6 +56,22 @@ QL_FN void ql_true_write_run(const QlClass& c, int k, const double* jv, double j
 #undef QL_TRUE_EXTRAS
 }
 
+// One knot's run of the VALS stream (layout.h: ql_vals_run_off): the value-dependent entries only, in column-major
+// order -- jv entries (rows masked by the jump Jacobian dropped) with d/dtheta of the body-clearance row after column 2.
+template <typename PTR>
+QL_FN void ql_vals_write_run(const QlClass& c, int k, const double* jv, double jtheta, PTR run)
+{
+    if (k == c.N) { QL_ST(run, 0, jtheta); return; }
+    if (k >= c.k_trans) ql_store_vals_mode3(jv, jtheta, run);
+    else if (k == c.k_trans - 1) {
+        if (c.init_mode == 1) ql_store_vals_mode1_jump(jv, jtheta, run);
+        else ql_store_vals_mode2_jump(jv, jtheta, run);
+    } else {
+        if (c.init_mode == 1) ql_store_vals_mode1(jv, jtheta, run);
+        else ql_store_vals_mode2(jv, jtheta, run);
+    }
+}
+
 // host-side enumeration helper: pattern (i, j) lists per variant, used by the structure generator
 struct QlTruePattern {
     int n;

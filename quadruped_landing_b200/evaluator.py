@@ -32,7 +32,11 @@ EXPORTED_SYMBOLS = (
     "qlnlp_eval_objective", "qlnlp_eval_objective_gradient", "qlnlp_eval_constraint",
     "qlnlp_eval_constraint_jacobian", "qlnlp_eval_batch_device", "qlnlp_eval_ragged_device", "qlnlp_eval_batch_host",
     "qlnlp_launch_info",
+    "qlnlp_create_multi", "qlnlp_devices", "qlnlp_shard_bounds", "qlnlp_set_option", "qlnlp_eval_all",
+    "qlnlp_eval_batch_device_multi", "qlnlp_synchronize", "qlnlp_host_output_register", "qlnlp_host_output_unregister",
+    "qlnlp_host_pin", "qlnlp_host_unpin", "qlnlp_host_path_info",
 )
+_DEBUG_SYMBOLS = ("qlnlp_debug_segments", "qlnlp_debug_vals_map", "qlnlp_debug_build_rows")
 
 
 class QlnlpError(RuntimeError):
@@ -99,7 +103,21 @@ def load_library(rebuild_if_stale: bool = True):
     L.qlnlp_eval_batch_host.argtypes = [vp, C.c_int64, C.POINTER(_BatchIO)]
     L.qlnlp_launch_info.argtypes = [vp, i64p]
     L.qlnlp_debug_segments.argtypes = [vp, vp, C.c_int64, i64p]
-    for name in EXPORTED_SYMBOLS[2:] + ("qlnlp_debug_segments",):
+    L.qlnlp_debug_vals_map.argtypes = [vp, vp, C.c_int64, i64p]
+    L.qlnlp_debug_build_rows.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int, C.c_int]
+    L.qlnlp_create_multi.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]
+    L.qlnlp_devices.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+    L.qlnlp_shard_bounds.argtypes = [C.c_int64, C.c_int, C.c_int, i64p, i64p]
+    L.qlnlp_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.qlnlp_eval_all.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.qlnlp_eval_batch_device_multi.argtypes = [vp, i64p, C.POINTER(_BatchIO), C.POINTER(vp)]
+    L.qlnlp_synchronize.argtypes = [vp]
+    L.qlnlp_host_output_register.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    L.qlnlp_host_output_unregister.argtypes = [vp, vp]
+    L.qlnlp_host_pin.argtypes = [vp, C.c_int64]
+    L.qlnlp_host_unpin.argtypes = [vp]
+    L.qlnlp_host_path_info.argtypes = [vp, i64p]
+    for name in [n for n in EXPORTED_SYMBOLS if n not in ("qlnlp_version", "qlnlp_last_error")] + list(_DEBUG_SYMBOLS):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -133,19 +151,23 @@ class HybridNLP:
 
     def __init__(self, model: PlanarQuadruped, obj: Sequence[QuadraticCost], init_mode: int, k_trans: int,
                  N: int, x0, xf, integration: str = "RK4", *, use_sparse_jacobian: bool = False,
-                 pattern: str = "block", device: int = 0):
+                 pattern: str = "block", device: int = 0, devices: Optional[Sequence[int]] = None):
         if integration != "RK4":
             raise ValueError("only RK4 is implemented (as in the reference)")
-        self._init(ProblemData.from_costs(model, obj, init_mode, k_trans, N, x0, xf), use_sparse_jacobian, device, pattern)
+        self._init(ProblemData.from_costs(model, obj, init_mode, k_trans, N, x0, xf), use_sparse_jacobian, device, pattern,
+                   devices)
 
     @classmethod
     def from_problem(cls, prob: ProblemData, *, use_sparse_jacobian: bool = True, pattern: str = "block",
-                     device: int = 0) -> "HybridNLP":
+                     device: int = 0, devices: Optional[Sequence[int]] = None) -> "HybridNLP":
+        """``devices=[0, 1, ...]`` builds a multi-device evaluator (``qlnlp_create_multi``): host-pointer batches are
+        sharded over the listed GPUs by the library, ``eval_batch_multi`` launches one shard per device."""
         self = cls.__new__(cls)
-        self._init(prob, use_sparse_jacobian, device, pattern)
+        self._init(prob, use_sparse_jacobian, device, pattern, devices)
         return self
 
-    def _init(self, prob: ProblemData, use_sparse_jacobian: bool, device: int, pattern: str = "block"):
+    def _init(self, prob: ProblemData, use_sparse_jacobian: bool, device: int, pattern: str = "block",
+              devices: Optional[Sequence[int]] = None):
         if pattern not in ("block", "true"):
             raise ValueError("pattern must be 'block' or 'true'")
         self.pattern = pattern
@@ -157,7 +179,8 @@ class HybridNLP:
         self.x0, self.xf = prob.x0, prob.xf
         self.modes = [prob.init_mode if k < prob.k_trans else 3 for k in range(1, prob.N + 1)]   # nlp.jl:42-44
         self.use_sparse_jacobian = bool(use_sparse_jacobian)
-        self.device = int(device)
+        self.devices = [int(x) for x in devices] if devices is not None else [int(device)]
+        self.device = self.devices[0]
         d = _Desc()
         d.N, d.k_trans, d.init_mode = prob.N, prob.k_trans, prob.init_mode
         m = prob.model
@@ -168,7 +191,12 @@ class HybridNLP:
         d.Q, d.R, d.q, d.r, d.c = (a.ctypes.data for a in (prob.Q, prob.R, prob.q, prob.r, prob.c))
         self._h = C.c_void_p()
         mode = JAC_DENSE if not use_sparse_jacobian else (JAC_SPARSE_TRUE if pattern == "true" else JAC_SPARSE_BLOCK)
-        _check(L.qlnlp_create(C.byref(d), self.device, mode, C.byref(self._h)))
+        if devices is None:
+            _check(L.qlnlp_create(C.byref(d), self.device, mode, C.byref(self._h)))
+        else:
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            _check(L.qlnlp_create_multi(C.byref(d), arr, len(self.devices), mode, C.byref(self._h)))
+        self._registered = {}
         n, mm, nnz, nnzb = (C.c_int64() for _ in range(4))
         _check(L.qlnlp_dims(self._h, C.byref(n), C.byref(mm), C.byref(nnz), C.byref(nnzb)))
         self.n_nlp, self.m_nlp, self.nnz, self.nnz_block = n.value, mm.value, nnz.value, nnzb.value
@@ -263,6 +291,44 @@ class HybridNLP:
         self._out(vec, self.nnz, "vec")
         _check(load_library().qlnlp_eval_constraint_jacobian(self._h, _np_ptr(self._x(x, self.n_nlp)), _np_ptr(vec)))
 
+    def eval_all(self, x, f: Optional[np.ndarray] = None, grad_f: Optional[np.ndarray] = None,
+                 g: Optional[np.ndarray] = None, vec: Optional[np.ndarray] = None) -> None:
+        """All four callbacks of one iterate with one launch (``qlnlp_eval_all``); any output may be omitted.
+        ``f`` is a 1-element array."""
+        if f is not None:
+            self._out(f, 1, "f")
+        if grad_f is not None:
+            self._out(grad_f, self.n_nlp, "grad_f")
+        if g is not None:
+            self._out(g, self.m_nlp, "g")
+        if vec is not None:
+            self._out(vec, self.nnz, "vec")
+        _check(load_library().qlnlp_eval_all(self._h, _np_ptr(self._x(x, self.n_nlp)), _np_ptr(f), _np_ptr(grad_f),
+                                             _np_ptr(g), _np_ptr(vec)))
+
+    def set_option(self, name: str, value: int) -> None:
+        _check(load_library().qlnlp_set_option(self._h, name.encode(), int(value)))
+
+    # ---- host-pointer path helpers
+    def register_host_output(self, jac: np.ndarray) -> None:
+        """``qlnlp_host_output_register``: write the constant image of the pattern into ``jac[B, nnz_batch]`` once;
+        later ``eval_batch_host(..., out={"jac": jac or a row-slice of it})`` rewrites only the lines that change."""
+        if not (isinstance(jac, np.ndarray) and jac.dtype == np.float64 and jac.ndim == 2 and jac.flags.c_contiguous
+                and jac.shape[1] == self.nnz_batch):
+            raise ValueError(f"jac must be a contiguous float64 array [B, {self.nnz_batch}]")
+        _check(load_library().qlnlp_host_output_register(self._h, jac.ctypes.data, jac.shape[1], jac.shape[0]))
+        self._registered[jac.ctypes.data] = jac          # keep it alive while it is registered
+
+    def unregister_host_output(self, jac: np.ndarray) -> None:
+        _check(load_library().qlnlp_host_output_unregister(self._h, jac.ctypes.data))
+        self._registered.pop(jac.ctypes.data, None)
+
+    def host_path_info(self) -> Dict[str, int]:
+        info = (C.c_int64 * 8)()
+        _check(load_library().qlnlp_host_path_info(self._h, info))
+        return dict(zip(("threads_per_device", "pcie_jac_doubles_per_eval", "row_doubles", "touched_lines_per_row",
+                         "lines_per_row", "avx512", "rows_built", "lines_written"), list(info)))
+
     # ---- batched evaluation
     def eval_batch(self, Z, *, x0=None, xf=None, want: Sequence[str] = ("f", "grad", "g", "jac"),
                    out: Optional[Dict[str, "object"]] = None, stream=None) -> Dict[str, "object"]:
@@ -316,6 +382,50 @@ class HybridNLP:
         s = torch.cuda.current_stream(dev) if stream is None else stream
         _check(load_library().qlnlp_eval_batch_device(self._h, B, C.byref(io), C.c_void_p(s.cuda_stream)))
         return out
+
+    def eval_batch_multi(self, Zs: Sequence["object"], *, want: Sequence[str] = ("f", "grad", "g", "jac"),
+                         outs: Optional[List[Dict[str, "object"]]] = None) -> List[Dict[str, "object"]]:
+        """One shard per device of a multi-device evaluator: ``Zs[i]`` is a float64 CUDA tensor ``[B_i, n_nlp]`` on
+        ``cuda:devices[i]``.  One ``qlnlp_eval_batch_device_multi`` call enqueues a fused launch on every device's
+        current torch stream; nothing is synchronised (``synchronize()`` waits for all devices)."""
+        import torch
+
+        nd = len(self.devices)
+        if len(Zs) != nd:
+            raise ValueError(f"need one Z per device ({nd})")
+        outs = [{} for _ in range(nd)] if outs is None else outs
+        ios = (_BatchIO * nd)()
+        Bs = (C.c_int64 * nd)()
+        streams = (C.c_void_p * nd)()
+        for i, (Z, out) in enumerate(zip(Zs, outs)):
+            if not (Z.is_cuda and Z.dtype == torch.float64 and Z.dim() == 2 and Z.shape[1] == self.n_nlp and Z.stride(1) == 1):
+                raise ValueError(f"Zs[{i}] must be a float64 CUDA tensor [B, {self.n_nlp}]")
+            if Z.device.index != self.devices[i]:
+                raise ValueError(f"Zs[{i}] lives on cuda:{Z.device.index}, shard {i} runs on cuda:{self.devices[i]}")
+            B = Z.shape[0]
+            Bs[i] = B
+            io = ios[i]
+            io.Z, io.ldz = Z.data_ptr(), Z.stride(0) if B > 1 else self.n_nlp
+            widths = {"grad": self.n_nlp, "g": self.m_nlp, "jac": self.nnz_batch}
+            if "f" in want:
+                if out.get("f") is None:
+                    out["f"] = torch.empty(B, dtype=torch.float64, device=Z.device)
+                io.f = out["f"].data_ptr()
+            for name, w in widths.items():
+                if name not in want:
+                    continue
+                t = out.get(name)
+                if t is None:
+                    t = torch.empty((B, even_ld(w)), dtype=torch.float64, device=Z.device)[:, :w]
+                    out[name] = t
+                setattr(io, name, t.data_ptr())
+                setattr(io, "ld" + name, t.stride(0) if B > 1 else even_ld(w))
+            streams[i] = torch.cuda.current_stream(Z.device).cuda_stream
+        _check(load_library().qlnlp_eval_batch_device_multi(self._h, Bs, ios, streams))
+        return outs
+
+    def synchronize(self) -> None:
+        _check(load_library().qlnlp_synchronize(self._h))
 
     def eval_ragged(self, index, flat: Dict[str, "object"], offsets: Dict[str, "object"], *, x0=None, xf=None,
                     stream=None, z_padded: bool = False) -> None:
@@ -387,6 +497,20 @@ class HybridNLP:
         info = (C.c_int64 * 5)()
         _check(load_library().qlnlp_launch_info(self._h, info))
         return dict(zip(("blocks", "threads_per_block", "smem_bytes", "blocks_per_sm", "sm_count"), list(info)))
+
+    def _debug_vals_map(self) -> np.ndarray:
+        n = C.c_int64()
+        L = load_library()
+        _check(L.qlnlp_debug_vals_map(self._h, None, 0, C.byref(n)))
+        pos = np.empty(n.value, dtype=np.int32)
+        _check(L.qlnlp_debug_vals_map(self._h, _np_ptr(pos), n.value, C.byref(n)))
+        return pos
+
+    def _debug_build_rows(self, vals: np.ndarray, jac: np.ndarray, touched_only: bool, threads: int = 1) -> None:
+        """The host row builder alone (CPU tests): rows of the batch pattern from VALS rows."""
+        assert vals.flags.c_contiguous and jac.dtype == np.float64 and jac.strides[-1] == 8
+        _check(load_library().qlnlp_debug_build_rows(self._h, _np_ptr(vals), vals.shape[1], jac.ctypes.data,
+                                                     jac.strides[0] // 8, jac.shape[0], int(touched_only), threads))
 
     def _debug_segments(self) -> np.ndarray:
         n = C.c_int64()

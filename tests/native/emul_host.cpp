@@ -23,12 +23,19 @@ int emul_jac_stream(int N, int k_trans, int init_mode, double g, double mb, doub
     ql_class_init(&c, N, k_trans, init_mode, g, mb, mf, lb);
     std::vector<double> bufs[2] = {std::vector<double>(QL_JBUF, NAN), std::vector<double>(QL_JBUF, NAN)};
     int tmpl[2] = {-1, -1};
-    for (int rep = 0; rep < (persist_templates ? 2 : 1); ++rep) {   // 2nd repetition reuses the images
+    unsigned segctr = 0;          // the kernel alternates the staging buffers with a running counter across evaluations
+    int last_buf = -1;
+    for (int rep = 0; rep < (persist_templates ? 3 : 1); ++rep) {   // later repetitions reuse the images
         for (int i = 0; i < c.nnz; ++i) out[i] = NAN;
         for (int s = 0; s < nseg; ++s) {
             const long long* sg = segs + 6 * s;
-            const int k0 = (int)sg[0], nk = (int)sg[1], start = (int)sg[2], end = (int)sg[3], tm = (int)sg[4], bi = (int)sg[5];
+            const int k0 = (int)sg[0], nk = (int)sg[1], start = (int)sg[2], end = (int)sg[3], tm = (int)sg[4];
+            const int bi = ql_seg_buffer(segctr++);
             if (bi < 0 || bi > 1 || nk < 1 || nk > 2) return -1;
+            // the bulk store committed just before may still be reading ITS buffer (wait_group.read 1): the buffer
+            // being rewritten must be the other one, also across the wrap from one evaluation to the next
+            if (bi == last_buf) return -3;
+            last_buf = bi;
             const int base = start & ~1;
             if (end - base > QL_JBUF) return -2;
             double* buf = bufs[bi].data();
@@ -96,6 +103,35 @@ int emul_true_stream(int N, int k_trans, int init_mode, double g, double mb, dou
         const int len = (k == N ? c.nnz_true : ql_true_run_off(c, k + 1)) - off;
         if (off < 0 || off + len > nout) return -2;
         ql_true_write_run(c, k, jv, jtheta, out + off);
+    }
+    return 0;
+}
+
+// VALS stream exactly as the kernel assembles it: every knot writes its value-dependent entries at ql_vals_run_off.
+int emul_vals_stream(int N, int k_trans, int init_mode, double g, double mb, double mf, double lb,
+                     const double* Z, double* out, int nout)
+{
+    QlClass c;
+    ql_class_init(&c, N, k_trans, init_mode, g, mb, mf, lb);
+    ql_class_finish(&c);
+    if (nout != c.nnz_vals) return -1;
+    const HostConsts K{c.g, c.mb, c.mf, c.Ib};
+    for (int i = 0; i < nout; ++i) out[i] = NAN;
+    for (int k = 1; k <= N; ++k) {
+        const double* x = Z + 20 * (k - 1);
+        double xn[15], jv[QL_NJ_MODE1];
+        if (k < N) {
+            const double* u = x + 15;
+            if (k >= k_trans) ql_rk4_jac_mode3(x, u, K, xn, jv);
+            else if (init_mode == 1) ql_rk4_jac_mode1(x, u, K, xn, jv);
+            else ql_rk4_jac_mode2(x, u, K, xn, jv);
+        }
+        const double th = x[2];
+        const double jtheta = (th > 0) ? (-c.half_lb) * std::cos(th) : c.half_lb * std::cos(th);
+        const int off = ql_vals_run_off(c, k);
+        if (off < 0 || off + ql_vals_len(c, k) > nout) return -2;
+        if (k < N && off + ql_vals_len(c, k) != ql_vals_run_off(c, k + 1)) return -3;
+        ql_vals_write_run(c, k, jv, jtheta, out + off);
     }
     return 0;
 }

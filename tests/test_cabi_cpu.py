@@ -28,7 +28,7 @@ def test_header_symbols_are_exported():
     L = ql.load_library()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.qlnlp_version() == 1
+    assert L.qlnlp_version() == 2
 
 
 def test_host_queries_work_without_a_device():

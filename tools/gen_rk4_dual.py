@@ -437,6 +437,29 @@ def main():
                         w(f"    QL_ST(p[{col_group(j)}], {off}, {repr(g.cval(xn[i].part(j)))});")
             w("}")
             w("")
+        # ---- VALS: only the value-dependent entries (what a host caller with a registered, pre-filled row needs) ----
+        # Run of a knot k < N: the jv entries in column-major order (masked rows dropped at the jump knot) with the
+        # body-clearance d/dtheta entry (constraints.jl:269-273) at its column-major place: after column 2.
+        for jump in ((0, 1) if mode != 3 else (0,)):
+            vj = [(n, i, j) for n, (i, j) in enumerate(var) if not (jump and not keep[i])]
+            tag = f"MODE{mode}" + ("_JUMP" if jump else "")
+            fn = f"mode{mode}" + ("_jump" if jump else "")
+            w(f"// VALS, {tag}: {len(vj)} value-dependent RK4 entries + d/dtheta")
+            w(f"#define QL_VALS_LEN_{tag} {len(vj) + 1}")
+            w(f"template <typename PTR>")
+            w(f"QL_FN void ql_store_vals_{fn}(const double* jv, double jtheta, PTR run)")
+            w("{")
+            pos, theta_done = 0, False
+            for n, i, j in vj:
+                if j >= 3 and not theta_done:
+                    w(f"    QL_ST(run, {pos}, jtheta);")
+                    pos += 1
+                    theta_done = True
+                w(f"    QL_ST(run, {pos}, jv[{n}]);")
+                pos += 1
+            assert theta_done and pos == len(vj) + 1
+            w("}")
+            w("")
         summary.append((mode, "jac", cnt, len(var), len(con)))
     text = "\n".join(out) + "\n"
     with open(OUT, "w") as f:
