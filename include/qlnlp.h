@@ -200,6 +200,11 @@ int qlnlp_host_output_unregister(qlnlp_handle h, double* jac);
 /* page-lock / unlock a caller-owned host array (cudaHostRegister) so that copies to and from it are asynchronous */
 int qlnlp_host_pin(void* ptr, int64_t bytes);
 int qlnlp_host_unpin(void* ptr);
+/* page-locked host memory on 2 MB pages where the kernel grants them (2 MB aligned, zero-filled).  Rows of 257 KB
+ * each touch 63 small pages; on a virtualised host the page walks of the row builder then cost as much as its stores.
+ * Free with qlnlp_host_free(ptr, same byte count). */
+int qlnlp_host_alloc(int64_t bytes, void** out);
+int qlnlp_host_free(void* ptr, int64_t bytes);
 /* host path facts: [0] row-builder threads per device, [1] Jacobian doubles per evaluation that cross PCIe,
  * [2] doubles per row, [3] 64-byte lines rewritten per registered row, [4] lines per row, [5] AVX-512 writer in use,
  * [6] rows assembled so far, [7] lines written so far */

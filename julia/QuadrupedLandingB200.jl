@@ -1,12 +1,21 @@
 # QuadrupedLandingB200.jl -- the reference-side binding of libqlnlp.so (include/qlnlp.h).
 #
-# Drop this file next to the reference's src/moi.jl and `include` it after src/nlp.jl: it defines
-# `CudaHybridNLP <: MOI.AbstractNLPEvaluator` with the same seven MOI methods as src/moi.jl:1-33, each a
-# one-line `ccall` into the C ABI, so `solve(Z0, CudaHybridNLP(nlp))` runs the unchanged Ipopt/MOI loop of
-# src/moi.jl:46-103 against the GPU evaluator.
+# ZERO-EDIT drop-in.  `include` this file after the reference's src/nlp.jl and src/moi.jl and call
 #
-# NOT EXECUTED in the build environment (no julia binary in the image).  The executable stand-in with the
-# same semantics is the ctypes wrapper quadruped_landing_b200/evaluator.py, which the test-suite drives.
+#     QuadrupedLandingB200.install!(nlp)                      # or install!(nlp; sparse=true, pattern=:true)
+#
+# `install!` builds a GPU evaluator for THIS `HybridNLP` object (src/nlp.jl:13-84), remembers it in an IdDict and
+# re-defines the seven `MOI.*(::HybridNLP, ...)` methods of src/moi.jl:1-33 so that they `ccall` the C ABI.  The
+# reference's `solve(Z0, nlp; ...)` (src/moi.jl:46-103) then runs UNCHANGED: it is typed to `HybridNLP`, reads
+# `num_primals(prob)`, `num_duals(prob)`, `prob.N`, `prob.lb`, `prob.ub` -- all still the reference's own -- and reaches
+# the evaluator only through the MOI callbacks.  With `sparse=true` the structure handed to Ipopt is the column-major
+# filter of the entries `jac_c!` assigns (32,161 pairs instead of the dense 1,327,995 of src/moi.jl:31-33, the reason
+# the recorded run spends 575 s inside Ipopt, src/main.ipynb:724); the default `sparse=false` reports exactly the
+# reference's dense structure.
+#
+# NOT EXECUTED in the build environment (no julia binary in the image).  tests/test_julia_shim.py checks every
+# `ccall` below (symbol, arity, argument and return types) and both struct layouts against include/qlnlp.h; the
+# executable twin with the same calls in the same order is quadruped_landing_b200/evaluator.py (ctypes).
 module QuadrupedLandingB200
 
 using MathOptInterface
@@ -14,7 +23,7 @@ const MOI = MathOptInterface
 
 const LIBQLNLP = get(ENV, "LIBQLNLP", "libqlnlp.so")
 
-# mirrors `qlnlp_model` / `qlnlp_problem_desc` of include/qlnlp.h field for field
+# mirrors `qlnlp_model` / `qlnlp_problem_desc` / `qlnlp_batch_io` of include/qlnlp.h field for field
 struct QlModel
     g::Cdouble; mb::Cdouble; mf::Cdouble; lb::Cdouble; l1::Cdouble; l2::Cdouble
 end
@@ -24,6 +33,14 @@ struct QlProblemDesc
     x0::NTuple{15,Cdouble}; xf::NTuple{15,Cdouble}
     Q::Ptr{Cdouble}; R::Ptr{Cdouble}; q::Ptr{Cdouble}; r::Ptr{Cdouble}; c::Ptr{Cdouble}
 end
+struct QlBatchIO
+    Z::Ptr{Cdouble}; ldz::Int64
+    x0::Ptr{Cdouble}; xf::Ptr{Cdouble}
+    f::Ptr{Cdouble}
+    grad::Ptr{Cdouble}; ldgrad::Int64
+    g::Ptr{Cdouble}; ldg::Int64
+    jac::Ptr{Cdouble}; ldjac::Int64
+end
 
 const JAC_SPARSE_BLOCK = Cint(0)
 const JAC_DENSE = Cint(1)
@@ -31,24 +48,25 @@ const JAC_SPARSE_TRUE = Cint(2)
 
 check(rc::Cint) = rc == 0 || error("qlnlp error $rc: " * unsafe_string(ccall((:qlnlp_last_error, LIBQLNLP), Cstring, ())))
 
-mutable struct CudaHybridNLP <: MOI.AbstractNLPEvaluator
+mutable struct GpuEvaluator
     handle::Ptr{Cvoid}
     n_nlp::Int
     m_nlp::Int
-    nnz::Int
-    keep::Vector{Any}     # cost tables referenced by the descriptor during qlnlp_create
+    nnz::Int          # values per evaluation in the handle's structure (dense: m_nlp * n_nlp)
+    nnz_batch::Int    # values per evaluation in batched calls (the handle's sparse pattern)
 end
 
-"""
-    CudaHybridNLP(nlp; sparse=true, pattern=:block, device=0)
+const HANDLES = IdDict{Any,GpuEvaluator}()
 
-Build the GPU evaluator from the reference's `HybridNLP` (src/nlp.jl:13-84).  `sparse=false` reports the
-dense m_nlp x n_nlp structure exactly like src/moi.jl:31-33; `sparse=true` reports SPARSE_BLOCK, the
-column-major filter of the entries `jac_c!` assigns (32,161 instead of 1,327,995 pairs at the default
-instance -- this is what removes the 575 s Ipopt spends on the dense structure, src/main.ipynb:724), or with
-`pattern=:true` only the 4,840 structurally non-zero entries.
 """
-function CudaHybridNLP(nlp; sparse::Bool=true, pattern::Symbol=:block, device::Integer=0)
+    GpuEvaluator(nlp; sparse=false, pattern=:block, device=0, devices=nothing)
+
+Build the GPU evaluator from the reference's `HybridNLP` (src/nlp.jl:13-84).  `sparse=false` reports the dense
+m_nlp x n_nlp structure exactly like src/moi.jl:31-33; `sparse=true` reports SPARSE_BLOCK, the column-major filter of
+the entries `jac_c!` assigns, or with `pattern=:true` only the 4,840 structurally non-zero entries.
+`devices=[0,1,...]` spreads host batches over several GPUs (qlnlp_create_multi).
+"""
+function GpuEvaluator(nlp; sparse::Bool=false, pattern::Symbol=:block, device::Integer=0, devices=nothing)
     N = nlp.N
     Q = Matrix{Cdouble}(undef, 15, N); R = Matrix{Cdouble}(undef, 5, N)
     q = Matrix{Cdouble}(undef, 15, N); r = Matrix{Cdouble}(undef, 5, N); c = Vector{Cdouble}(undef, N)
@@ -59,56 +77,126 @@ function CudaHybridNLP(nlp; sparse::Bool=true, pattern::Symbol=:block, device::I
     m = nlp.model
     desc = Ref(QlProblemDesc(N, nlp.k_trans, nlp.init_mode, QlModel(m.g, m.mb, m.mf, m.lb, m.l1, m.l2),
                              Tuple(nlp.x0), Tuple(nlp.xf), pointer(Q), pointer(R), pointer(q), pointer(r), pointer(c)))
+    mode = sparse ? (pattern == :true ? JAC_SPARSE_TRUE : JAC_SPARSE_BLOCK) : JAC_DENSE
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve Q R q r c check(ccall((:qlnlp_create, LIBQLNLP), Cint,
-        (Ref{QlProblemDesc}, Cint, Cint, Ref{Ptr{Cvoid}}), desc, device,
-        sparse ? (pattern == :true ? JAC_SPARSE_TRUE : JAC_SPARSE_BLOCK) : JAC_DENSE, h))
+    GC.@preserve Q R q r c begin      # the descriptor's tables are copied during creation, not retained
+        if devices === nothing
+            check(ccall((:qlnlp_create, LIBQLNLP), Cint, (Ref{QlProblemDesc}, Cint, Cint, Ref{Ptr{Cvoid}}),
+                        desc, device, mode, h))
+        else
+            devs = Vector{Cint}(devices)
+            check(ccall((:qlnlp_create_multi, LIBQLNLP), Cint, (Ref{QlProblemDesc}, Ptr{Cint}, Cint, Cint, Ref{Ptr{Cvoid}}),
+                        desc, devs, length(devs), mode, h))
+        end
+    end
     n = Ref{Int64}(0); mm = Ref{Int64}(0); nnz = Ref{Int64}(0); nb = Ref{Int64}(0)
     check(ccall((:qlnlp_dims, LIBQLNLP), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Int64}), h[], n, mm, nnz, nb))
-    ev = CudaHybridNLP(h[], n[], mm[], nnz[], Any[Q, R, q, r, c])
+    ev = GpuEvaluator(h[], n[], mm[], nnz[], sparse ? nnz[] : nb[])
     finalizer(e -> ccall((:qlnlp_destroy, LIBQLNLP), Cint, (Ptr{Cvoid},), e.handle), ev)
     return ev
 end
 
-num_primals(p::CudaHybridNLP) = p.n_nlp          # src/nlp.jl:86
-num_duals(p::CudaHybridNLP) = p.m_nlp            # src/nlp.jl:87
-
-# ---- the seven MOI methods of src/moi.jl:1-33 ------------------------------------------------
-function MOI.eval_objective(prob::CudaHybridNLP, x)                       # moi.jl:1-3
+# ---- the callbacks, one `ccall` each -------------------------------------------------------------------------
+function gpu_eval_objective(ev::GpuEvaluator, x)                              # moi.jl:1-3
     f = Ref{Cdouble}(0.0)
-    check(ccall((:qlnlp_eval_objective, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ref{Cdouble}), prob.handle, x, f))
+    check(ccall((:qlnlp_eval_objective, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ref{Cdouble}), ev.handle, x, f))
+    return f[]
+end
+function gpu_eval_objective_gradient(ev::GpuEvaluator, grad_f, x)             # moi.jl:5-8
+    check(ccall((:qlnlp_eval_objective_gradient, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), ev.handle, x, grad_f))
+    return nothing
+end
+function gpu_eval_constraint(ev::GpuEvaluator, g, x)                          # moi.jl:10-13
+    check(ccall((:qlnlp_eval_constraint, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), ev.handle, x, g))
+    return nothing
+end
+function gpu_eval_constraint_jacobian(ev::GpuEvaluator, vec, x)               # moi.jl:15-24
+    check(ccall((:qlnlp_eval_constraint_jacobian, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), ev.handle, x, vec))
+    return nothing
+end
+function gpu_jacobian_structure(ev::GpuEvaluator)                             # moi.jl:31-33
+    rows = Vector{Int64}(undef, ev.nnz); cols = Vector{Int64}(undef, ev.nnz)
+    check(ccall((:qlnlp_jacobian_structure, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), ev.handle, rows, cols))
+    return collect(zip(rows, cols))                                           # 1-based (row, col), value order
+end
+# f, grad f, g and the Jacobian values of one iterate with one launch (the callbacks above share that launch anyway:
+# the library serves callbacks at an unchanged x from its last evaluation)
+function gpu_eval_all!(ev::GpuEvaluator, x, grad_f, g, vec)
+    f = Ref{Cdouble}(0.0)
+    check(ccall((:qlnlp_eval_all, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                ev.handle, x, f, grad_f, g, vec))
     return f[]
 end
 
-function MOI.eval_objective_gradient(prob::CudaHybridNLP, grad_f, x)      # moi.jl:5-8
-    check(ccall((:qlnlp_eval_objective_gradient, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), prob.handle, x, grad_f))
-    return nothing
-end
-
-function MOI.eval_constraint(prob::CudaHybridNLP, g, x)                   # moi.jl:10-13
-    check(ccall((:qlnlp_eval_constraint, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), prob.handle, x, g))
-    return nothing
-end
-
-function MOI.eval_constraint_jacobian(prob::CudaHybridNLP, vec, x)        # moi.jl:15-24
-    check(ccall((:qlnlp_eval_constraint_jacobian, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), prob.handle, x, vec))
-    return nothing
-end
-
-MOI.features_available(prob::CudaHybridNLP) = [:Grad, :Jac]               # moi.jl:26-28
-MOI.initialize(prob::CudaHybridNLP, features) = nothing                   # moi.jl:30
-
-function MOI.jacobian_structure(prob::CudaHybridNLP)                      # moi.jl:31-33
-    rows = Vector{Int64}(undef, prob.nnz); cols = Vector{Int64}(undef, prob.nnz)
-    check(ccall((:qlnlp_jacobian_structure, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), prob.handle, rows, cols))
-    return collect(zip(rows, cols))                                       # 1-based (row, col), value order
-end
-
-# constraint bounds for MOI.NLPBoundsPair.(c_l, c_u) in solve(), src/moi.jl:69-74 / src/nlp.jl:66-69
-function constraint_bounds(prob::CudaHybridNLP)
-    lb = Vector{Cdouble}(undef, prob.m_nlp); ub = similar(lb)
-    check(ccall((:qlnlp_constraint_bounds, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), prob.handle, lb, ub))
+# constraint / variable bounds as the library restates them (src/nlp.jl:66-69, src/moi.jl:51-67); solve() keeps using
+# the reference's own prob.lb / prob.ub, these are for callers that build the bounds themselves
+function constraint_bounds(ev::GpuEvaluator)
+    lb = Vector{Cdouble}(undef, ev.m_nlp); ub = similar(lb)
+    check(ccall((:qlnlp_constraint_bounds, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), ev.handle, lb, ub))
     return lb, ub
 end
+function variable_bounds(ev::GpuEvaluator)
+    xl = Vector{Cdouble}(undef, ev.n_nlp); xu = similar(xl)
+    check(ccall((:qlnlp_variable_bounds, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), ev.handle, xl, xu))
+    return xl, xu
+end
+
+"""
+    eval_batch_host!(ev, Z; f, grad, g, jac)
+
+B decision vectors at once on host arrays: `Z` is `n_nlp x B` (one decision vector per COLUMN, i.e. the row-major
+`[B][n_nlp]` layout of the C ABI), `f` a `B`-vector, `grad` `n_nlp x B`, `g` `m_nlp x B`, `jac` `nnz_batch x B`; pass
+`nothing` to skip an output.  Multi-start guesses, line-search trial points and sweeps go through here.
+"""
+function eval_batch_host!(ev::GpuEvaluator, Z::Matrix{Cdouble}; f=nothing, grad=nothing, g=nothing, jac=nothing)
+    B = size(Z, 2)
+    p(a) = a === nothing ? Ptr{Cdouble}(C_NULL) : pointer(a)
+    ld(a) = a === nothing ? Int64(0) : Int64(size(a, 1))
+    io = Ref(QlBatchIO(pointer(Z), size(Z, 1), C_NULL, C_NULL, p(f), p(grad), ld(grad), p(g), ld(g), p(jac), ld(jac)))
+    GC.@preserve Z f grad g jac check(ccall((:qlnlp_eval_batch_host, LIBQLNLP), Cint, (Ptr{Cvoid}, Int64, Ref{QlBatchIO}), ev.handle, B, io))
+    return nothing
+end
+
+# a `jac` matrix that is reused for every batch: its structural zeros and +-1 entries are written once, later batches
+# rewrite only the lines that change (like jac_c! relying on the caller's zeros, constraints.jl:212-291)
+register_output!(ev::GpuEvaluator, jac::Matrix{Cdouble}) =
+    check(ccall((:qlnlp_host_output_register, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64), ev.handle, jac, size(jac, 1), size(jac, 2)))
+unregister_output!(ev::GpuEvaluator, jac::Matrix{Cdouble}) =
+    check(ccall((:qlnlp_host_output_unregister, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), ev.handle, jac))
+# page-lock a Julia array so that the copies to and from the GPU are asynchronous
+pin!(a::Array{Cdouble}) = check(ccall((:qlnlp_host_pin, LIBQLNLP), Cint, (Ptr{Cvoid}, Int64), a, sizeof(a)))
+unpin!(a::Array{Cdouble}) = check(ccall((:qlnlp_host_unpin, LIBQLNLP), Cint, (Ptr{Cvoid},), a))
+
+evaluator(nlp) = get(HANDLES, nlp) do
+    error("no GPU evaluator installed for this HybridNLP: call QuadrupedLandingB200.install!(nlp) first")
+end
+
+"""
+    install!(nlp; sparse=false, pattern=:block, device=0, devices=nothing, into=Main)
+
+Make `nlp` (a `HybridNLP` of the reference) evaluate on the GPU.  Re-defines, in module `into` (where the reference's
+src/nlp.jl and src/moi.jl were included), the seven MOI methods of src/moi.jl:1-33 for `::HybridNLP`; afterwards
+`solve(Z0, nlp; c_tol=1e-3, tol=1e-3)` (src/main.ipynb:742-744, src/moi.jl:46-103) runs without any edit.
+Every `HybridNLP` handed to MOI after this call needs its own `install!`.
+"""
+function install!(nlp; into::Module=Main, kwargs...)
+    HANDLES[nlp] = GpuEvaluator(nlp; kwargs...)
+    Core.eval(into, quote
+        $MOI.eval_objective(prob::HybridNLP, x) =
+            $gpu_eval_objective($evaluator(prob), x)                                          # moi.jl:1-3
+        $MOI.eval_objective_gradient(prob::HybridNLP, grad_f, x) =
+            $gpu_eval_objective_gradient($evaluator(prob), grad_f, x)                         # moi.jl:5-8
+        $MOI.eval_constraint(prob::HybridNLP, g, x) =
+            $gpu_eval_constraint($evaluator(prob), g, x)                                      # moi.jl:10-13
+        $MOI.eval_constraint_jacobian(prob::HybridNLP, vec, x) =
+            $gpu_eval_constraint_jacobian($evaluator(prob), vec, x)                           # moi.jl:15-24 (uses `prob`, not the global `nlp`)
+        $MOI.features_available(prob::HybridNLP) = [:Grad, :Jac]                               # moi.jl:26-28
+        $MOI.initialize(prob::HybridNLP, features) = nothing                                   # moi.jl:30
+        $MOI.jacobian_structure(prob::HybridNLP) = $gpu_jacobian_structure($evaluator(prob))   # moi.jl:31-33
+    end)
+    return HANDLES[nlp]
+end
+
+uninstall!(nlp) = (delete!(HANDLES, nlp); nothing)
 
 end # module

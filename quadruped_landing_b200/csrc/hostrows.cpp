@@ -102,6 +102,29 @@ void Pool::parallel_for(int64_t n, int64_t block, const std::function<void(int64
     while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
 }
 
+void Pool::start(int64_t n, int64_t block, std::function<void(int64_t, int64_t)> fn)
+{
+    if (n <= 0) return;
+    if (workers_.empty()) { fn(0, n); return; }
+    finish();
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        owned_ = std::move(fn);
+        fn_ = &owned_;
+        n_ = n;
+        block_ = std::max<int64_t>(1, block);
+        next_.store(0, std::memory_order_relaxed);
+        pending_.store((int)workers_.size(), std::memory_order_relaxed);
+        epoch_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+}
+
+void Pool::finish()
+{
+    while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
+}
+
 // ================================================================================================ Worker
 Worker::Worker()
 {
@@ -240,6 +263,7 @@ RowPlan::RowPlan(int64_t nnz, const double* tmpl, int64_t nvals, const int32_t* 
         A.nlines = rest / 8;
         A.tail = (int)(rest % 8);
         A.mask.assign((size_t)A.nlines, 0);
+        A.konst.assign((size_t)A.nlines, 0);
         int64_t vi = 0;
         for (int e = 0; e < A.head; ++e) vi += vd_[(size_t)e];
         for (int64_t l = 0; l < A.nlines; ++l) {
@@ -247,9 +271,11 @@ RowPlan::RowPlan(int64_t nnz, const double* tmpl, int64_t nvals, const int32_t* 
             unsigned m = 0;
             for (int e = 0; e < 8; ++e) m |= (unsigned)vd_[(size_t)(base + e)] << e;
             A.mask[(size_t)l] = (uint8_t)m;
+            uint8_t k = 0;
+            for (int e = 0; e < 8; ++e) k |= (tmpl_[(size_t)(base + e)] != 0.0) ? 1 : 0;
+            A.konst[(size_t)l] = k;
             if (m) {
-                A.touched.push_back((uint32_t)l);
-                A.src0.push_back((uint32_t)vi);
+                A.touched.push_back({(uint32_t)l, (uint32_t)vi, (uint8_t)m, k});
                 vi += __builtin_popcount(m);
             }
         }
@@ -285,7 +311,7 @@ void RowPlan::row_generic(const Aligned& A, const double* in, double* out, bool 
         return v0;
     };
     if (touched_only) {
-        for (size_t t = 0; t < A.touched.size(); ++t) line(A.touched[t], A.src0[t]);
+        for (size_t t = 0; t < A.touched.size(); ++t) line(A.touched[t].line, A.touched[t].src);
     } else {
         for (int64_t l = 0; l < A.nlines; ++l) vi = line(l, vi);
     }
@@ -310,20 +336,23 @@ __attribute__((target("avx512f"))) void RowPlan::row_avx512(const Aligned& A, co
     const double* tl = tm + A.head;
     double* ol = out + A.head;                      // 64-byte aligned by construction
     if (touched_only) {
-        const uint32_t* lines = A.touched.data();
-        const uint32_t* src0 = A.src0.data();
+        const Touched* tt = A.touched.data();
         const size_t nt = A.touched.size();
         for (size_t t = 0; t < nt; ++t) {
-            const int64_t l = lines[t];
-            const __mmask8 m = (__mmask8)A.mask[(size_t)l];
-            const __m512d v = _mm512_mask_expandloadu_pd(_mm512_loadu_pd(tl + 8 * l), m, in + src0[t]);
+            const Touched e = tt[t];
+            const int64_t l = e.line;
+            // most lines hold no constant besides zeros: their image needs no load
+            const __m512d v = e.konst ? _mm512_mask_expandloadu_pd(_mm512_loadu_pd(tl + 8 * l), (__mmask8)e.mask, in + e.src)
+                                      : _mm512_maskz_expandloadu_pd((__mmask8)e.mask, in + e.src);
             _mm512_stream_pd(ol + 8 * l, v);
         }
     } else {
         const uint8_t* mask = A.mask.data();
+        const uint8_t* konst = A.konst.data();
         for (int64_t l = 0; l < A.nlines; ++l) {
             const __mmask8 m = (__mmask8)mask[l];
-            const __m512d v = _mm512_mask_expandloadu_pd(_mm512_loadu_pd(tl + 8 * l), m, in + vi);
+            const __m512d v = konst[l] ? _mm512_mask_expandloadu_pd(_mm512_loadu_pd(tl + 8 * l), m, in + vi)
+                                       : _mm512_maskz_expandloadu_pd(m, in + vi);
             vi += __builtin_popcount((unsigned)m);
             _mm512_stream_pd(ol + 8 * l, v);
         }
@@ -361,6 +390,13 @@ void RowPlan::build(Pool* pool, const double* vals, int64_t ldv, double* out, in
 {
     if (!pool) { build_rows(vals, ldv, out, ldout, 0, rows, touched_only); return; }
     pool->parallel_for(rows, 4, [&](int64_t a, int64_t b) { build_rows(vals, ldv, out, ldout, a, b, touched_only); });
+}
+
+void RowPlan::build_async(Pool* pool, const double* vals, int64_t ldv, double* out, int64_t ldout, int64_t rows,
+                          bool touched_only) const
+{
+    if (!pool) { build_rows(vals, ldv, out, ldout, 0, rows, touched_only); return; }
+    pool->start(rows, 2, [=](int64_t a, int64_t b) { build_rows(vals, ldv, out, ldout, a, b, touched_only); });
 }
 
 }  // namespace qlhost

@@ -25,6 +25,11 @@ public:
     ~Pool();
     int size() const { return (int)workers_.size() + 1; }
     void parallel_for(int64_t n, int64_t block, const std::function<void(int64_t, int64_t)>& fn);
+    // The same job on the WORKERS only: returns at once, so the caller can keep feeding the GPU; busy() / finish()
+    // tell when it is done.  One job at a time.  A pool without workers runs the job inside start().
+    void start(int64_t n, int64_t block, std::function<void(int64_t, int64_t)> fn);
+    bool busy() const { return pending_.load(std::memory_order_acquire) != 0; }
+    void finish();
 
 private:
     void worker_main(int idx, int cpu);
@@ -37,6 +42,7 @@ private:
     std::atomic<int64_t> next_{0};
     int64_t n_ = 0, block_ = 1;
     const std::function<void(int64_t, int64_t)>* fn_ = nullptr;
+    std::function<void(int64_t, int64_t)> owned_;           // the job of start()
     bool stop_ = false;
 };
 
@@ -78,6 +84,8 @@ std::vector<int> cpu_slice(const std::vector<int>& cpus, int part, int nparts);
 class RowPlan {
 public:
     RowPlan(int64_t nnz, const double* tmpl, int64_t nvals, const int32_t* pos);
+    // rows on the pool's workers, asynchronously (Pool::start); the arrays must stay valid until pool->finish()
+    void build_async(Pool* pool, const double* vals, int64_t ldv, double* out, int64_t ldout, int64_t rows, bool touched_only) const;
     int64_t nnz() const { return nnz_; }
     int64_t nvals() const { return nvals_; }
     // lines (64 B) rewritten per row in TOUCHED mode for a row that starts `a` doubles into a line
@@ -89,12 +97,18 @@ public:
     static bool have_avx512();
 
 private:
+    struct Touched {                      // one 64-byte line that holds value-dependent entries
+        uint32_t line;                    // line index inside the row
+        uint32_t src;                     // VALS index of its first value
+        uint8_t mask;                     // which of its 8 elements are value-dependent
+        uint8_t konst;                    // 1: its constant image is not all zeros
+    };
     struct Aligned {                      // per row alignment a = (address / 8) % 8
         int head = 0, tail = 0;           // scalar elements before the first / after the last full line
         int64_t nlines = 0;
         std::vector<uint8_t> mask;        // [nlines] bit e set: element e of the line is value-dependent
-        std::vector<uint32_t> touched;    // lines with mask != 0
-        std::vector<uint32_t> src0;       // [touched.size()] VALS index of the first value of that line
+        std::vector<uint8_t> konst;       // [nlines] 1: the constant image of the line is not all zeros
+        std::vector<Touched> touched;     // the lines with mask != 0, in order (what a registered row rewrites)
         int64_t tail_src = 0;             // VALS index of the first value-dependent tail element
     };
     const Aligned& aligned(int a) const { return al_[a]; }

@@ -4,8 +4,10 @@
 #include "../../include/qlnlp.h"
 
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -45,7 +47,7 @@ int fail(int code, const char* fmt, ...)
 
 constexpr int TICKET_POOL = 64;
 constexpr int NJM = 4;                 // kernel value streams: JM_NONE, JM_BLOCK, JM_TRUE, JM_VALS
-constexpr int MAX_LANES = 3;           // pipeline depth of the host-pointer path
+constexpr int MAX_LANES = 4;           // pipeline depth of the host-pointer path
 constexpr int64_t COMPACT_MIN_B = 64;  // below this, host-pointer batches copy the pattern rows as they are
 
 // Every entry point that touches the device makes the handle's device current and restores the caller's on exit
@@ -79,6 +81,9 @@ struct OneEval {
     double* hout = nullptr;
     double* dx = nullptr;       // device: x (padded row)
     double* dout = nullptr;     // device: f(2) | grad(ldz_e) | g(ldg_e) | vals(ldv_e)
+    bool zero_copy = false;     // the kernel reads x from / writes the results to the pinned block itself (mapped memory)
+    double* mx = nullptr;       // device-side addresses of hx / hout when zero_copy
+    double* mout = nullptr;
     int64_t o_grad = 0, o_g = 0, o_vals = 0, total = 0;
     bool valid = false;         // hout holds the results for the x stored in hx
 };
@@ -136,6 +141,7 @@ struct qlnlp_handle_s {
     int64_t opt_x_cache = 1;
     int64_t ldz_e = 0, ldgrad_e = 0, ldg_e = 0, ldjac_e = 0, ldv_e = 0;   // even leading dimensions of the scratch
     int64_t stat_host_rows = 0, stat_host_lines = 0;                     // rows / 64-byte lines the row builder wrote
+    double stat_t_enqueue = 0, stat_t_wait = 0, stat_t_build = 0, stat_t_total = 0;   // seconds, host-pointer batches
 };
 
 namespace {
@@ -363,6 +369,12 @@ int env_int(const char* name, int dflt)
     return dflt;
 }
 
+bool env_flag(const char* name, bool dflt)
+{
+    const char* e = std::getenv(name);
+    return (e && *e) ? std::atoi(e) != 0 : dflt;
+}
+
 // The worker pool of this handle: its share of the CPUs the process may use.  With one process per GPU (torchrun)
 // the ranks of a node split the cores (LOCAL_RANK of LOCAL_WORLD_SIZE); a multi-device handle splits its share
 // again between its devices; on a multi-socket host the share is taken from the CPUs next to the GPU.
@@ -387,7 +399,7 @@ int ensure_pool(qlnlp_handle h)
     if (h->opt_host_threads > 0) T = (int)h->opt_host_threads;
     T = env_int("QLNLP_HOST_THREADS", T);
     T = std::max(1, std::min(T, 256));
-    const bool pin = h->opt_pin_threads != 0 && env_int("QLNLP_PIN_THREADS", 1) != 0 && !std::getenv("QLNLP_NO_PIN");
+    const bool pin = h->opt_pin_threads != 0 && env_flag("QLNLP_PIN_THREADS", true);
     h->pool.reset(new (std::nothrow) qlhost::Pool(T, mine, pin));
     if (!h->pool) return fail(QLNLP_ENOMEM, "out of host memory");
     return QLNLP_OK;
@@ -446,11 +458,24 @@ int ensure_device(qlnlp_handle h)
             int nb = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, h->smem[wj]));
             if (nb < 1) return fail(QLNLP_ECUDA, "kernel does not fit on an SM");
-            if (const char* env = std::getenv("QLNLP_BLOCKS_PER_SM")) {       // tuning knob: fewer resident warps per SM
+            const char* env = std::getenv("QLNLP_BLOCKS_PER_SM");              // tuning knob: fewer resident warps per SM
+            if (env) {
                 const int cap = std::atoi(env);
                 if (cap >= 1 && cap < nb) nb = cap;
             }
             h->blocks_per_sm[wj] = rg ? std::min(h->blocks_per_sm[wj], nb) : nb;
+            // Shared memory the resident warps really need: whatever the SM has beyond that serves as L1 (the cost
+            // table and the boundary states are re-read by every warp).  The attribute belongs to the FUNCTION, so it
+            // only ever grows (handles of other horizons share it).
+            {
+                static std::map<const void*, size_t> g_need;
+                const int used = (wj == ql::JM_BLOCK && !env) ? std::min(nb, 6) : nb;      // see launch()
+                size_t& need = g_need[fn];
+                need = std::max(need, (size_t)used * (h->smem[wj] + 1024));
+                const int pct = (int)std::min<size_t>(100, need * 100 / (size_t)prop.sharedMemPerMultiprocessor + 2);
+                if (!std::getenv("QLNLP_MAX_CARVEOUT"))
+                    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            }
         }
     }
     for (auto& ln : h->lanes) {
@@ -631,55 +656,92 @@ int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
         touched_only = is_registered(h, io->jac, io->ldjac, B);
     }
     const int nnz_b = batch_nnz(h);
+    // Device-side leading dimensions.  Padded (even) rows give the kernel its TMA / 16-byte paths, but when the caller's
+    // rows are tightly packed a padded device copy needs a PITCHED transfer (one DMA descriptor per 9.7 KB row: 36 GB/s
+    // instead of 50+).  PCIe is what bounds this path, not the kernel: mirror the caller's packing.
+    const int64_t ldz_d = (io->ldz == c.n_nlp) ? c.n_nlp : h->ldz_e;
+    const int64_t ldgrad_d = (io->grad && io->ldgrad == c.n_nlp) ? c.n_nlp : h->ldgrad_e;
+    const int64_t ldg_d = (io->g && io->ldg == c.m_nlp) ? c.m_nlp : h->ldg_e;
+    const int64_t ldjac_d = (io->jac && io->ldjac == nnz_b) ? nnz_b : h->ldjac_e;      // uncompacted rows only
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
 
     auto enqueue = [&](int64_t i) -> int {
+        const double t0 = now();
         HostLane& ln = h->lanes[i % nlanes];
         const int64_t b0 = i * chunk, nb = std::min(chunk, B - b0);
         cudaStream_t s = ln.stream;
-        CUDA_TRY(copy_rows(ln.Z, h->ldz_e, io->Z + b0 * io->ldz, io->ldz, c.n_nlp, nb, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(copy_rows(ln.Z, ldz_d, io->Z + b0 * io->ldz, io->ldz, c.n_nlp, nb, cudaMemcpyHostToDevice, s));
         if (io->x0) CUDA_TRY(cudaMemcpyAsync(ln.x0, io->x0 + b0 * QL_NX, sizeof(double) * nb * QL_NX, cudaMemcpyHostToDevice, s));
         if (io->xf) CUDA_TRY(cudaMemcpyAsync(ln.xf, io->xf + b0 * QL_NX, sizeof(double) * nb * QL_NX, cudaMemcpyHostToDevice, s));
         qlnlp_batch_io d;
         std::memset(&d, 0, sizeof d);
-        d.Z = ln.Z; d.ldz = h->ldz_e;
+        d.Z = ln.Z; d.ldz = ldz_d;
         d.x0 = io->x0 ? ln.x0 : nullptr;
         d.xf = io->xf ? ln.xf : nullptr;
         d.f = io->f ? ln.f : nullptr;
-        d.grad = io->grad ? ln.grad : nullptr; d.ldgrad = h->ldgrad_e;
-        d.g = io->g ? ln.g : nullptr; d.ldg = h->ldg_e;
-        d.jac = io->jac ? ln.jac : nullptr; d.ldjac = compact ? h->ldv_e : h->ldjac_e;
+        d.grad = io->grad ? ln.grad : nullptr; d.ldgrad = ldgrad_d;
+        d.g = io->g ? ln.g : nullptr; d.ldg = ldg_d;
+        d.jac = io->jac ? ln.jac : nullptr; d.ldjac = compact ? h->ldv_e : ldjac_d;
         if (int rc = launch(h, nb, &d, s, compact ? ql::JM_VALS : -1)) return rc;
         if (io->f) CUDA_TRY(cudaMemcpyAsync(io->f + b0, ln.f, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
-        if (io->grad) CUDA_TRY(copy_rows(io->grad + b0 * io->ldgrad, io->ldgrad, ln.grad, h->ldgrad_e, c.n_nlp, nb, cudaMemcpyDeviceToHost, s));
-        if (io->g) CUDA_TRY(copy_rows(io->g + b0 * io->ldg, io->ldg, ln.g, h->ldg_e, c.m_nlp, nb, cudaMemcpyDeviceToHost, s));
+        if (io->grad) CUDA_TRY(copy_rows(io->grad + b0 * io->ldgrad, io->ldgrad, ln.grad, ldgrad_d, c.n_nlp, nb, cudaMemcpyDeviceToHost, s));
+        if (io->g) CUDA_TRY(copy_rows(io->g + b0 * io->ldg, io->ldg, ln.g, ldg_d, c.m_nlp, nb, cudaMemcpyDeviceToHost, s));
         if (compact) {
             CUDA_TRY(cudaMemcpyAsync(ln.stage, ln.jac, sizeof(double) * nb * h->ldv_e, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaEventRecord(ln.done, s));
         } else if (io->jac) {
-            CUDA_TRY(copy_rows(io->jac + b0 * io->ldjac, io->ldjac, ln.jac, h->ldjac_e, nnz_b, nb, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(copy_rows(io->jac + b0 * io->ldjac, io->ldjac, ln.jac, ldjac_d, nnz_b, nb, cudaMemcpyDeviceToHost, s));
+        }
+        h->stat_t_enqueue += now() - t0;
+        return QLNLP_OK;
+    };
+    // Row assembly runs on the pool's workers while this thread keeps the device fed: chunk j is handed to the pool
+    // as soon as its copies have landed and the pool is free; chunk i may be enqueued once chunk i - nlanes has been
+    // assembled (its pinned stage is reused).
+    int64_t enq = 0, handed = 0, built = 0;
+    double t_build0 = 0;
+    auto progress = [&](bool may_block) -> int {
+        if (!compact) { handed = built = enq; return QLNLP_OK; }
+        if (handed > built) {                                   // a build is running
+            if (h->pool->busy()) {
+                if (!may_block) return QLNLP_OK;
+                h->pool->finish();
+            }
+            ++built;
+            h->stat_t_build += now() - t_build0;
+        }
+        if (handed == built && handed < enq) {
+            HostLane& ln = h->lanes[handed % nlanes];
+            const double t0 = now();
+            cudaError_t q = may_block ? cudaEventSynchronize(ln.done) : cudaEventQuery(ln.done);
+            h->stat_t_wait += now() - t0;
+            if (q == cudaErrorNotReady) return QLNLP_OK;
+            if (q != cudaSuccess) return fail(QLNLP_ECUDA, "host pipeline: %s", cudaGetErrorString(q));
+            const int64_t b0 = handed * chunk, nb = std::min(chunk, B - b0);
+            double* rows = io->jac + b0 * io->ldjac;
+            t_build0 = now();
+            h->plan->build_async(h->pool.get(), ln.stage, h->ldv_e, rows, io->ldjac, nb, touched_only);
+            ++handed;
+            h->stat_host_rows += nb;
+            h->stat_host_lines += nb * (touched_only ? h->plan->touched_lines((int)((reinterpret_cast<uintptr_t>(rows) >> 3) & 7))
+                                                     : (h->plan->nnz() + 7) / 8);
         }
         return QLNLP_OK;
     };
-    auto finish = [&](int64_t i) -> int {
-        if (!compact) return QLNLP_OK;
-        HostLane& ln = h->lanes[i % nlanes];
-        const int64_t b0 = i * chunk, nb = std::min(chunk, B - b0);
-        CUDA_TRY(cudaEventSynchronize(ln.done));
-        double* rows = io->jac + b0 * io->ldjac;
-        h->plan->build(h->pool.get(), ln.stage, h->ldv_e, rows, io->ldjac, nb, touched_only);
-        h->stat_host_rows += nb;
-        h->stat_host_lines += nb * (touched_only ? h->plan->touched_lines((int)((reinterpret_cast<uintptr_t>(rows) >> 3) & 7))
-                                                 : (h->plan->nnz() + 7) / 8);
-        return QLNLP_OK;
-    };
     for (int64_t i = 0; i < nchunks; ++i) {
-        if (i >= nlanes)
-            if (int rc = finish(i - nlanes)) return rc;      // frees the lane chunk i is about to use
+        while (compact && i - built >= nlanes)
+            if (int rc = progress(true)) return rc;
         if (int rc = enqueue(i)) return rc;
+        ++enq;
+        if (int rc = progress(false)) return rc;
     }
-    for (int64_t i = std::max<int64_t>(0, nchunks - nlanes); i < nchunks; ++i)
-        if (int rc = finish(i)) return rc;
+    while (built < enq)
+        if (int rc = progress(true)) return rc;
+    const double t_sync = now();
     for (int l = 0; l < nlanes; ++l) CUDA_TRY(cudaStreamSynchronize(h->lanes[l].stream));
+    h->stat_t_wait += now() - t_sync;
+    h->stat_t_total += now() - t_begin;
     return QLNLP_OK;
 }
 
@@ -701,6 +763,7 @@ int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
         // copies into caller-owned host memory (and out of the pinned stage) may still be in flight: finish them
         // before the caller gets its buffers back
         const std::string msg = g_err;
+        if (h->pool) h->pool->finish();
         for (auto& ln : h->lanes)
             if (ln.stream) cudaStreamSynchronize(ln.stream);
         cudaGetLastError();
@@ -741,8 +804,21 @@ int reserve_one(qlnlp_handle h)
     o.o_g = o.o_grad + h->ldgrad_e;
     o.o_vals = o.o_g + h->ldg_e;
     o.total = o.o_vals + h->ldv_e;
-    CUDA_TRY(cudaHostAlloc(&o.hx, sizeof(double) * (h->ldz_e + o.total), cudaHostAllocDefault));
+    // One decision vector is latency-bound: with mapped pinned memory the kernel fetches x and stores its 41 KB of
+    // results over PCIe itself, which saves the two copy calls (QLNLP_ONE_ZEROCOPY=0 goes back to explicit copies).
+    o.zero_copy = env_flag("QLNLP_ONE_ZEROCOPY", true);
+    CUDA_TRY(cudaHostAlloc(&o.hx, sizeof(double) * (h->ldz_e + o.total), o.zero_copy ? cudaHostAllocMapped : cudaHostAllocDefault));
     o.hout = o.hx + h->ldz_e;
+    if (o.zero_copy) {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, o.hx, 0) == cudaSuccess && dp) {
+            o.mx = static_cast<double*>(dp);
+            o.mout = o.mx + h->ldz_e;
+        } else {
+            cudaGetLastError();
+            o.zero_copy = false;
+        }
+    }
     CUDA_TRY(cudaMalloc(&o.dx, sizeof(double) * h->ldz_e));
     CUDA_TRY(cudaMalloc(&o.dout, sizeof(double) * o.total));
     o.valid = false;
@@ -769,16 +845,18 @@ int eval_one(qlnlp_handle hh, const double* x, double* f, double* grad, double* 
         o.valid = false;
         std::memcpy(o.hx, x, sizeof(double) * c.n_nlp);
         cudaStream_t s = o.stream;
-        CUDA_TRY(cudaMemcpyAsync(o.dx, o.hx, sizeof(double) * c.n_nlp, cudaMemcpyHostToDevice, s));
+        double* const zin = o.zero_copy ? o.mx : o.dx;
+        double* const res = o.zero_copy ? o.mout : o.dout;
+        if (!o.zero_copy) CUDA_TRY(cudaMemcpyAsync(o.dx, o.hx, sizeof(double) * c.n_nlp, cudaMemcpyHostToDevice, s));
         qlnlp_batch_io d;
         std::memset(&d, 0, sizeof d);
-        d.Z = o.dx; d.ldz = h->ldz_e;
-        d.f = o.dout;
-        d.grad = o.dout + o.o_grad; d.ldgrad = h->ldgrad_e;
-        d.g = o.dout + o.o_g; d.ldg = h->ldg_e;
-        d.jac = o.dout + o.o_vals; d.ldjac = h->ldv_e;
+        d.Z = zin; d.ldz = o.zero_copy ? c.n_nlp : h->ldz_e;        // odd ld: plain (non-TMA) loads from host memory
+        d.f = res;
+        d.grad = res + o.o_grad; d.ldgrad = h->ldgrad_e;
+        d.g = res + o.o_g; d.ldg = h->ldg_e;
+        d.jac = res + o.o_vals; d.ldjac = o.zero_copy ? h->ldv_e + 1 : h->ldv_e;   // odd ld: plain stores into host memory
         if (int rc = launch(h, 1, &d, s, ql::JM_VALS)) return rc;
-        CUDA_TRY(cudaMemcpyAsync(o.hout, o.dout, sizeof(double) * o.total, cudaMemcpyDeviceToHost, s));
+        if (!o.zero_copy) CUDA_TRY(cudaMemcpyAsync(o.hout, o.dout, sizeof(double) * o.total, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         o.valid = true;
     }
@@ -1168,6 +1246,50 @@ int qlnlp_host_unpin(void* ptr)
     return QLNLP_OK;
 }
 
+/* Page-locked host memory on 2 MB pages where the kernel grants them (madvise MADV_HUGEPAGE): rows of 257 KB each
+ * touch 63 small pages, and on a virtualised host the page walks of a row builder that hops from line to line cost as
+ * much as the stores.  The allocation is 2 MB aligned, zero-filled and registered with CUDA. */
+int qlnlp_host_alloc(int64_t bytes, void** out)
+{
+    if (!out || bytes <= 0) return fail(QLNLP_EINVAL, "bad allocation request");
+    *out = nullptr;
+    const size_t huge = (size_t)2 << 20;
+    const size_t len = ((size_t)bytes + huge - 1) / huge * huge;
+    void* raw = mmap(nullptr, len + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (raw == MAP_FAILED) return fail(QLNLP_ENOMEM, "mmap of %zu bytes failed", len + huge);
+    char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(raw) + huge - 1) / huge * huge);
+    // give back the unaligned head and tail so that the mapping is exactly [base, base + len)
+    if (base > (char*)raw) munmap(raw, (size_t)(base - (char*)raw));
+    char* end = (char*)raw + len + huge;
+    if (end > base + len) munmap(base + len, (size_t)(end - (base + len)));
+#ifdef MADV_HUGEPAGE
+    madvise(base, len, MADV_HUGEPAGE);        // best effort
+#endif
+    std::memset(base, 0, len);                // fault the pages in (as huge pages where possible) before pinning them
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+        cudaError_t e = cudaHostRegister(base, len, cudaHostRegisterPortable);
+        if (e != cudaSuccess) {
+            munmap(base, len);
+            return fail(QLNLP_ECUDA, "cudaHostRegister of %zu bytes: %s", len, cudaGetErrorString(e));
+        }
+    } else {
+        cudaGetLastError();                   // no device: plain (unpinned) memory, still usable by the CPU-side tests
+    }
+    *out = base;
+    return QLNLP_OK;
+}
+
+int qlnlp_host_free(void* ptr, int64_t bytes)
+{
+    if (!ptr) return QLNLP_OK;
+    const size_t huge = (size_t)2 << 20;
+    const size_t len = ((size_t)bytes + huge - 1) / huge * huge;
+    if (cudaHostUnregister(ptr) != cudaSuccess) cudaGetLastError();
+    munmap(ptr, len);
+    return QLNLP_OK;
+}
+
 int qlnlp_eval_all(qlnlp_handle h, const double* x, double* f, double* grad, double* g, double* vals)
 {
     if (int rc = check_handle(h)) return rc;
@@ -1233,6 +1355,16 @@ int qlnlp_host_path_info(qlnlp_handle h, int64_t info[8])
     info[5] = qlhost::RowPlan::have_avx512() ? 1 : 0;
     info[6] = rows;                                   // rows assembled so far
     info[7] = lines;                                  // lines written so far
+    return QLNLP_OK;
+}
+
+/* seconds spent so far by host-pointer batches of the first device: [0] total, [1] enqueueing copies and launches,
+ * [2] waiting for the device / PCIe, [3] assembling rows (not part of the public header: tools/e2e_probe.py) */
+int qlnlp_debug_host_times(qlnlp_handle h, double out[4])
+{
+    if (int rc = check_handle(h)) return rc;
+    qlnlp_handle s = first(h);
+    out[0] = s->stat_t_total; out[1] = s->stat_t_enqueue; out[2] = s->stat_t_wait; out[3] = s->stat_t_build;
     return QLNLP_OK;
 }
 

@@ -34,6 +34,9 @@
 
 #include "layout.h"
 
+#ifndef QL_TRUE_WARPS
+#define QL_TRUE_WARPS 8      // resident-warp target of the SPARSE_TRUE / VALS instantiations (252 registers at 8)
+#endif
 #ifndef QL_NONE_WARPS
 #define QL_NONE_WARPS 16     // resident-warp target (register cap: 128) of the instantiation without a Jacobian:
                              // 16 warps/SM give +23..28 % over 8 (f+grad+g / g only), 20+ spill and lose
@@ -84,6 +87,11 @@ __device__ __forceinline__ void bulk_load(unsigned sdst, const void* gsrc, unsig
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst),
                  "l"(gsrc), "r"(bytes), "r"(mbar)
                  : "memory");
+}
+// ask L2 to fetch a row that a later TMA load will want (the ticket of the next evaluation is known early)
+__device__ __forceinline__ void prefetch_l2(const void* gsrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 // g / grad rows are written once and never re-read by the kernel: streaming (evict-first) stores, +0.6 % in A/B runs
 #define QL_GST(ptr, v) __stcs((ptr), (v))
@@ -173,6 +181,7 @@ struct Launch {
 
 // shared memory carve-up: staged Z (same layout as in HBM) | mbarrier | two J staging buffers | segment plan
 __host__ __device__ inline int zbuf_len(int N) { return QL_NZK * N + 2; }     // n_nlp + 1 rounded up to even, + mbarrier
+#define QL_FBUF 32           // per-lane cost terms of a pass, summed in knot order (costs.jl:9-15)
 enum { JM_NONE = 0, JM_BLOCK = 1, JM_TRUE = 2, JM_VALS = 3 };     // which Jacobian value stream the kernel produces
 static_assert(QL_VALS_LEN_MODE1 == QL_VALS_LEN_INIT && QL_VALS_LEN_MODE2 == QL_VALS_LEN_INIT &&
               QL_VALS_LEN_MODE1_JUMP == QL_VALS_LEN_JUMPK && QL_VALS_LEN_MODE2_JUMP == QL_VALS_LEN_JUMPK &&
@@ -186,7 +195,7 @@ __host__ __device__ inline size_t smem_jregion_bytes(int N, int jm)
 }
 __host__ __device__ inline size_t smem_bytes(int N, int jm)
 {
-    return sizeof(double) * (size_t)zbuf_len(N) + smem_jregion_bytes(N, jm);
+    return sizeof(double) * (size_t)(zbuf_len(N) + QL_FBUF) + smem_jregion_bytes(N, jm);
 }
 
 // Start fetching a decision vector into shared memory.  zbulk: one TMA bulk load of n+1 doubles (n is odd, the
@@ -205,7 +214,7 @@ __device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigne
 }
 
 template <int JM, bool FASTDIV, bool RAGGED>
-__global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) eval_kernel(const __grid_constant__ Launch P)
+__global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM == JM_BLOCK ? 8 : QL_TRUE_WARPS)) eval_kernel(const __grid_constant__ Launch P)
 {
     constexpr bool WITH_JAC = JM != JM_NONE;
     extern __shared__ __align__(16) double smem[];
@@ -214,7 +223,8 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
 
     double* const zbuf = smem;
     const unsigned mbar = smem_addr(zbuf + zbuf_len(c.N) - 1);      // 8-byte mbarrier behind the staged vector
-    double* const jb = zbuf + zbuf_len(c.N);
+    double* const fbuf = zbuf + zbuf_len(c.N);
+    double* const jb = fbuf + QL_FBUF;
     QlSeg* const plan = reinterpret_cast<QlSeg*>(jb + 2 * QL_JBUF);
     const unsigned zaddr = smem_addr(zbuf);
     const unsigned jaddr = smem_addr(jb);
@@ -265,7 +275,10 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
         double fsum = 0.0;
         // the kernels without the SPARSE_BLOCK stream are latency-bound: take the next ticket now, so that the atomic's
         // round trip is hidden behind this evaluation (the SPARSE_BLOCK kernel has no register to spare for it)
-        if (JM != JM_BLOCK) nb = take();
+        if (JM != JM_BLOCK) {
+            nb = take();
+            if (zbulk && nb < P.B && lane == 0) prefetch_l2(zrow_of(nb), 8u * (unsigned)(c.n_nlp + 1));
+        }
         const long long pi = (RAGGED && P.index) ? __ldg(P.index + b) : b;      // problem number (f, x0, xf, offsets)
         double* const grow = P.g ? P.g + (RAGGED ? __ldg(P.g_off + pi) : b * P.ldg) : nullptr;
         double* const gradrow = P.grad ? P.grad + (RAGGED ? __ldg(P.z_off + pi) : b * P.ldgrad) : nullptr;
@@ -273,6 +286,14 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
         // TMA bulk stores need 16-byte aligned rows: a launch-wide property for strided batches, per row when ragged
         const bool bulk = P.bulk != 0 && (!RAGGED || (reinterpret_cast<uintptr_t>(jrow) & 15) == 0);
 
+        if (grow) {
+            // boundary rows (constraints.jl:149-150) straight from the staged vector, one lane per row
+            const double* x0 = P.x0 ? P.x0 + pi * QL_NX : P.x0_def;
+            const double* xf = P.xf ? P.xf + pi * QL_NX : P.xf_def;
+            if (lane < QL_NX) grow[lane] = __dsub_rn(zbuf[lane], __ldg(x0 + lane));
+            if (lane < QL_NX - 1) grow[c.c_term + lane] = __dsub_rn(zbuf[(c.N - 1) * QL_NZK + lane], __ldg(xf + lane));
+            __syncwarp();
+        }
         for (int p = 0; p < c.npass; ++p) {
             const int k = p * QL_LANES + lane + 1;          // 1-based knot of this lane
             const bool act = k <= c.N;
@@ -315,10 +336,14 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                     hq = __dadd_rn(hq, __dmul_rn(__dmul_rn(0.5, __dmul_rn(xk[i], cq[i])), xk[i]));
                     dq = __dadd_rn(dq, __dmul_rn(cq[15 + i], xk[i]));
                 }
+                // my knot's slice of the gradient goes in place over my (dead) slice of the staged Z, as 16-byte stores
+                double2* const zk2 = reinterpret_cast<double2*>(zk);
+                double gz[QL_NZK];
 #pragma unroll
                 for (int i = 0; i < QL_NX; ++i) {
                     const double gq = __dadd_rn(__dmul_rn(cq[i], xk[i]), cq[15 + i]);       // Q*x + q
-                    zk[i] = has_u ? __dmul_rn(hk, gq) : gq;
+                    gz[i] = has_u ? __dmul_rn(hk, gq) : gq;
+                    if ((i & 1) && gradrow) zk2[i >> 1] = make_double2(gz[i - 1], gz[i]);
                 }
                 double term;
                 if (has_u) {
@@ -332,22 +357,35 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                     // quirk Q1 (costs.jl:30): the h entry gets h*(R55*h + r5), not d(h*stagecost)/dh
 #pragma unroll
                     for (int i = 0; i < QL_NU; ++i)
-                        zk[QL_NX + i] = __dmul_rn(hk, __dadd_rn(__dmul_rn(cq[30 + i], uk[i]), cq[35 + i]));
+                        gz[QL_NX + i] = __dmul_rn(hk, __dadd_rn(__dmul_rn(cq[30 + i], uk[i]), cq[35 + i]));
                     // ((((0.5x'Qx + q'x) + 0.5u'Ru) + r'u) + c) * h
                     const double sc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(hq, dq), hr), dr), cq[40]);
                     term = __dmul_rn(hk, sc);
                 } else {
                     term = __dadd_rn(__dadd_rn(hq, dq), cq[40]);       // termcost
+#pragma unroll
+                    for (int i = 0; i < QL_NU; ++i) gz[QL_NX + i] = 0.0;       // lands beyond n_nlp in the staging area
+                }
+                if (gradrow) {
+#pragma unroll
+                    for (int i = QL_NX / 2; i < QL_NZK / 2; ++i) zk2[i] = make_double2(gz[2 * i], gz[2 * i + 1]);
                 }
                 lane_term = term;
             }
             if (P.f) {
-                // costs.jl:9-15 accumulates J knot by knot: do the same (every lane computes the same sum)
-#pragma unroll 8
-                for (int s = 0; s < QL_LANES; ++s) {
-                    const double t = __shfl_sync(0xffffffffu, lane_term, s);
-                    if (p * QL_LANES + s < c.N) fsum = __dadd_rn(fsum, t);
+                // costs.jl:9-15 accumulates J knot by knot: do the same, through shared memory (every lane adds up
+                // the same sequence; only lane 0's copy is stored)
+                fbuf[lane] = lane_term;
+                __syncwarp();
+                const int nact = min(QL_LANES, c.N - p * QL_LANES);
+                const double2* f2 = reinterpret_cast<const double2*>(fbuf);
+                int s = 0;
+                for (; s + 1 < nact; s += 2) {
+                    const double2 t = f2[s >> 1];
+                    fsum = __dadd_rn(__dadd_rn(fsum, t.x), t.y);
                 }
+                if (s < nact) fsum = __dadd_rn(fsum, fbuf[s]);
+                __syncwarp();
             }
 
             // flush this pass's gradient slice with coalesced stores; the slice is then free for the defects
@@ -402,16 +440,6 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : 8) e
                     grow[c.c_cfirst + (k - 1)] = first_is_y1 ? xk[4] : xk[6];                                   // :58/:60
                     if (k >= c.k_trans) grow[c.c_cother + (k - c.k_trans)] = first_is_y1 ? xk[6] : xk[4];      // :84/:86
                     grow[c.c_body + (k - 1)] = __dsub_rn(xk[1], __dmul_rn(c.half_lb, fabs(s)));                 // :109
-                    if (k == 1) {
-                        const double* x0 = P.x0 ? P.x0 + pi * QL_NX : P.x0_def;
-#pragma unroll
-                        for (int i = 0; i < QL_NX; ++i) grow[i] = __dsub_rn(xk[i], __ldg(x0 + i));        // :149
-                    }
-                    if (k == c.N) {
-                        const double* xf = P.xf ? P.xf + pi * QL_NX : P.xf_def;
-#pragma unroll
-                        for (int i = 0; i < QL_NX - 1; ++i) grow[c.c_term + i] = __dsub_rn(xk[i], __ldg(xf + i));   // :150
-                    }
                     if (k == c.N - 1) grow[c.c_fctrl] = __dadd_rn(__dadd_rn(uk[1], uk[3]), c.mbg);       // :154
                 }
             }

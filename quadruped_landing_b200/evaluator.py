@@ -34,9 +34,9 @@ EXPORTED_SYMBOLS = (
     "qlnlp_launch_info",
     "qlnlp_create_multi", "qlnlp_devices", "qlnlp_shard_bounds", "qlnlp_set_option", "qlnlp_eval_all",
     "qlnlp_eval_batch_device_multi", "qlnlp_synchronize", "qlnlp_host_output_register", "qlnlp_host_output_unregister",
-    "qlnlp_host_pin", "qlnlp_host_unpin", "qlnlp_host_path_info",
+    "qlnlp_host_pin", "qlnlp_host_unpin", "qlnlp_host_path_info", "qlnlp_host_alloc", "qlnlp_host_free",
 )
-_DEBUG_SYMBOLS = ("qlnlp_debug_segments", "qlnlp_debug_vals_map", "qlnlp_debug_build_rows")
+_DEBUG_SYMBOLS = ("qlnlp_debug_segments", "qlnlp_debug_vals_map", "qlnlp_debug_build_rows", "qlnlp_debug_host_times")
 
 
 class QlnlpError(RuntimeError):
@@ -105,6 +105,7 @@ def load_library(rebuild_if_stale: bool = True):
     L.qlnlp_debug_segments.argtypes = [vp, vp, C.c_int64, i64p]
     L.qlnlp_debug_vals_map.argtypes = [vp, vp, C.c_int64, i64p]
     L.qlnlp_debug_build_rows.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int, C.c_int]
+    L.qlnlp_debug_host_times.argtypes = [vp, C.POINTER(C.c_double)]
     L.qlnlp_create_multi.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]
     L.qlnlp_devices.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
     L.qlnlp_shard_bounds.argtypes = [C.c_int64, C.c_int, C.c_int, i64p, i64p]
@@ -117,10 +118,49 @@ def load_library(rebuild_if_stale: bool = True):
     L.qlnlp_host_pin.argtypes = [vp, C.c_int64]
     L.qlnlp_host_unpin.argtypes = [vp]
     L.qlnlp_host_path_info.argtypes = [vp, i64p]
+    L.qlnlp_host_alloc.argtypes = [C.c_int64, C.POINTER(vp)]
+    L.qlnlp_host_free.argtypes = [vp, C.c_int64]
     for name in [n for n in EXPORTED_SYMBOLS if n not in ("qlnlp_version", "qlnlp_last_error")] + list(_DEBUG_SYMBOLS):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
+
+
+class _HostBlock:
+    """Owner of a qlnlp_host_alloc block; numpy arrays made from it keep it alive through their ``base``."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        self.ptr = C.c_void_p()
+        rc = load_library().qlnlp_host_alloc(self.nbytes, C.byref(self.ptr))
+        if rc != QLNLP_OK:
+            raise QlnlpError(rc, load_library().qlnlp_last_error().decode())
+        self.buf = (C.c_char * self.nbytes).from_address(self.ptr.value)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) is not None and self.ptr.value and _lib is not None:
+            _lib.qlnlp_host_free(self.ptr, self.nbytes)
+            self.ptr = C.c_void_p()
+
+
+def host_alloc(shape, dtype=np.float64) -> np.ndarray:
+    """A zero-filled numpy array in page-locked host memory on 2 MB pages where the kernel grants them
+    (``qlnlp_host_alloc``): the preferred home of the arrays handed to ``eval_batch_host``."""
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    blk = _HostBlock(max(n, 1))
+    a = np.frombuffer(blk.buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    a.flags.writeable = True
+    _host_blocks[a.ctypes.data] = blk            # ctypes buffers do not keep python attributes: keep the owner here
+    return a
+
+
+_host_blocks = {}
+
+
+def host_free(a: np.ndarray) -> None:
+    """Release an array made by ``host_alloc`` (the array must not be used afterwards)."""
+    _host_blocks.pop(a.ctypes.data, None)
 
 
 def _check(rc: int):
@@ -497,6 +537,11 @@ class HybridNLP:
         info = (C.c_int64 * 5)()
         _check(load_library().qlnlp_launch_info(self._h, info))
         return dict(zip(("blocks", "threads_per_block", "smem_bytes", "blocks_per_sm", "sm_count"), list(info)))
+
+    def _debug_host_times(self) -> Dict[str, float]:
+        t = (C.c_double * 4)()
+        _check(load_library().qlnlp_debug_host_times(self._h, t))
+        return dict(zip(("total", "enqueue", "wait", "build"), list(t)))
 
     def _debug_vals_map(self) -> np.ndarray:
         n = C.c_int64()

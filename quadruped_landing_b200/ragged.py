@@ -26,6 +26,8 @@ class RaggedEvaluator:
         self.m = np.array([e.m_nlp for e in self.nlps], dtype=np.int64)
         self.nnz = np.array([e.nnz_block for e in self.nlps], dtype=np.int64)
         self._streams = None
+        self._plan = None
+        self.launches_per_eval = len(self.nlps)        # one fused launch per class
 
     def offsets(self, class_of: np.ndarray) -> Dict[str, np.ndarray]:
         """Row starts (in doubles): problem b owns Z[z_off[b] : z_off[b] + n_b], g[g_off[b] : ...], jac[j_off[b] : ...].
@@ -44,44 +46,68 @@ class RaggedEvaluator:
             Z[off[b]:off[b] + len(v)] = v
         return Z
 
-    def eval(self, class_of: np.ndarray, Z_flat, want=("f", "grad", "g", "jac")):
-        """``Z_flat``: 1-D float64 CUDA tensor holding the decision vectors back to back (see ``offsets``).
-        Returns flat CUDA tensors ``f[B]``, ``grad`` (Z layout), ``g``, ``jac`` and the offset tables.
+    def plan(self, class_of: np.ndarray, device=None) -> "RaggedPlan":
+        """Everything about a batch that does not depend on the decision vectors: the offset tables and each class's
+        problem list, uploaded once.  ``eval`` caches the plan of the last ``class_of`` it saw, so repeated
+        evaluations of one batch (solver iterations) do no per-call host work."""
+        import torch
+
+        class_of = np.ascontiguousarray(class_of, dtype=np.int64)
+        dev = torch.device("cuda", self.device) if device is None else device
+        off = self.offsets(class_of)
+        doff = {k: torch.from_numpy(v).to(dev) for k, v in off.items()}
+        index = []
+        for c in range(len(self.nlps)):
+            idx = np.nonzero(class_of == c)[0]
+            index.append(torch.from_numpy(idx).to(dev) if idx.size else None)
+        return RaggedPlan(class_of.copy(), off, doff, index)
+
+    def eval(self, class_of, Z_flat, want=("f", "grad", "g", "jac"), out=None):
+        """``Z_flat``: 1-D float64 CUDA tensor holding the decision vectors back to back (see ``offsets``);
+        ``class_of``: the class index of every problem, or a ``RaggedPlan``.  Returns flat CUDA tensors ``f[B]``,
+        ``grad`` (Z layout), ``g``, ``jac`` and the offset tables; pass the returned dict back as ``out`` to reuse
+        the output arrays.
 
         Every class is one ``qlnlp_eval_ragged_device`` launch on its own stream: the kernel addresses each
         problem's rows through the offset tables, so nothing is gathered or scattered."""
         import torch
 
-        class_of = np.asarray(class_of, dtype=np.int64)
-        B = class_of.shape[0]
-        off = self.offsets(class_of)
         dev = Z_flat.device
+        if isinstance(class_of, RaggedPlan):
+            plan = class_of
+        else:
+            class_of = np.ascontiguousarray(class_of, dtype=np.int64)
+            plan = self._plan
+            if plan is None or plan.class_of.shape != class_of.shape or not np.array_equal(plan.class_of, class_of):
+                plan = self._plan = self.plan(class_of, dev)
+        B = plan.class_of.shape[0]
+        off = plan.off
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=dev) for _ in self.nlps]
         flat = {"Z": Z_flat}
-        if "f" in want:
-            flat["f"] = torch.empty(B, dtype=torch.float64, device=dev)
-        if "grad" in want:
-            flat["grad"] = torch.empty(int(off["z_off"][-1]), dtype=torch.float64, device=dev)
-        if "g" in want:
-            flat["g"] = torch.empty(int(off["g_off"][-1]), dtype=torch.float64, device=dev)
-        if "jac" in want:
-            flat["jac"] = torch.empty(int(off["j_off"][-1]), dtype=torch.float64, device=dev)
-        doff = {k: torch.from_numpy(v).to(dev) for k, v in off.items()}
+        sizes = {"f": B, "grad": int(off["z_off"][-1]), "g": int(off["g_off"][-1]), "jac": int(off["j_off"][-1])}
+        for name in ("f", "grad", "g", "jac"):
+            if name in want:
+                t = None if out is None else out.get(name)
+                if t is None or t.numel() != sizes[name] or t.device != dev:
+                    t = torch.empty(sizes[name], dtype=torch.float64, device=dev)
+                flat[name] = t
         cur = torch.cuda.current_stream(dev)
-        keep = []
         for c, nlp in enumerate(self.nlps):
-            idx = np.nonzero(class_of == c)[0]
-            if idx.size == 0:
+            if plan.index[c] is None:
                 continue
             s = self._streams[c]
             s.wait_stream(cur)
-            with torch.cuda.stream(s):
-                index = torch.from_numpy(idx).to(dev)
-                nlp.eval_ragged(index, flat, doff, stream=s, z_padded=True)
-                keep.append(index)
+            nlp.eval_ragged(plan.index[c], flat, plan.doff, stream=s, z_padded=True)
             cur.wait_stream(s)
-        out = {k: v for k, v in flat.items() if k != "Z"}
-        out.update(off)
-        self._keep = (keep, doff)          # alive until the next call: the launches are asynchronous
-        return out
+        res = {k: v for k, v in flat.items() if k != "Z"}
+        res.update(off)
+        self._keep = plan                  # alive until the next call: the launches are asynchronous
+        return res
+
+
+class RaggedPlan:
+    """Offset tables (host + device) and per-class problem lists of one mixed batch (``RaggedEvaluator.plan``)."""
+
+    def __init__(self, class_of, off, doff, index):
+        self.class_of, self.off, self.doff, self.index = class_of, off, doff, index

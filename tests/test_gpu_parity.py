@@ -351,7 +351,7 @@ def test_host_batch_compact_transfer_rebuilds_exact_rows(golden):
         assert np.array_equal(host["g"], devr["g"][lo:hi]) and np.array_equal(host["f"], devr["f"][lo:hi])
     after = nlp.host_path_info()
     lines = after["lines_written"] - before["lines_written"]
-    assert lines <= (1100 + 1100 + 800) * (after["touched_lines_per_row"] + 2)      # really the touched lines only
+    assert lines <= (1100 + 1100 + 800) * 1800 < 3000 * after["lines_per_row"] / 2     # the touched lines only (<= 1742 per row, any alignment)
     nlp.unregister_host_output(jac)
     host = nlp.eval_batch_host(Z[:300], out={"jac": jac[:300]})
     assert np.array_equal(jac[:300], dev["jac"][:300])
