@@ -646,8 +646,8 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "check": e2e_check,
                     "path": "qlnlp_eval_batch_host on pinned host buffers, output rows registered once "
-                            "(qlnlp_host_output_register, like jac_c! relying on the caller's zeros): 256-evaluation chunks "
-                            "pipelined over 3 streams; f/grad/g land in the caller's arrays by DMA; of the 32,161 SPARSE_BLOCK "
+                            "(qlnlp_host_output_register, like jac_c! relying on the caller's zeros): 512-evaluation chunks "
+                            "pipelined over 4 streams; f/grad/g land in the caller's arrays by DMA; of the 32,161 SPARSE_BLOCK "
                             "values per evaluation only the 2,794 value-dependent ones cross PCIe and a persistent pool of host "
                             "threads rewrites the 64-byte lines that hold them (non-temporal AVX-512 stores, no arithmetic)",
                     "pcie_d2h_bytes_per_step": pcie_d2h, "host_bytes_written_per_step": host_bytes,

@@ -24,19 +24,27 @@ typedef double Number;
 typedef int Index;
 typedef int Bool;
 
+/* Ipopt passes new_x = FALSE when x is the vector of the previous callback.  The library does the bookkeeping itself:
+ * the first callback at a new x evaluates f, grad f, g and the Jacobian values with ONE launch and the callbacks that
+ * follow at the same x are served from that evaluation (qlnlp.h, "single evaluations"), so the four callbacks of an
+ * iterate cost one H2D + one kernel + one D2H.  new_x is honoured on top of that: when Ipopt says the vector is new
+ * the whole bundle is requested at once through qlnlp_eval_all into the callback's own output. */
 static Bool eval_f(Index n, Number* x, Bool new_x, Number* obj_value, void* user_data)
 {
-    (void)n; (void)new_x;
+    (void)n;
+    if (new_x) return qlnlp_eval_all((qlnlp_handle)user_data, x, obj_value, NULL, NULL, NULL) == QLNLP_OK;
     return qlnlp_eval_objective((qlnlp_handle)user_data, x, obj_value) == QLNLP_OK;
 }
 static Bool eval_grad_f(Index n, Number* x, Bool new_x, Number* grad_f, void* user_data)
 {
-    (void)n; (void)new_x;
+    (void)n;
+    if (new_x) return qlnlp_eval_all((qlnlp_handle)user_data, x, NULL, grad_f, NULL, NULL) == QLNLP_OK;
     return qlnlp_eval_objective_gradient((qlnlp_handle)user_data, x, grad_f) == QLNLP_OK;
 }
 static Bool eval_g(Index n, Number* x, Bool new_x, Index m, Number* g, void* user_data)
 {
-    (void)n; (void)new_x; (void)m;
+    (void)n; (void)m;
+    if (new_x) return qlnlp_eval_all((qlnlp_handle)user_data, x, NULL, NULL, g, NULL) == QLNLP_OK;
     return qlnlp_eval_constraint((qlnlp_handle)user_data, x, g) == QLNLP_OK;
 }
 /* structure call (values == NULL) or value call; Ipopt's C interface uses 0-based or 1-based indices by option */
@@ -119,9 +127,10 @@ int main(void)
 
     double f, *grad = malloc(sizeof(double) * n), *g = malloc(sizeof(double) * m), *vals = malloc(sizeof(double) * nnz);
     Index* iRow = malloc(sizeof(Index) * nnz), *jCol = malloc(sizeof(Index) * nnz);
-    if (!eval_f((Index)n, Z, 1, &f, h) || !eval_grad_f((Index)n, Z, 1, grad, h) || !eval_g((Index)n, Z, 1, (Index)m, g, h) ||
-        !eval_jac_g((Index)n, Z, 1, (Index)m, (Index)nnz, iRow, jCol, NULL, h) ||
-        !eval_jac_g((Index)n, Z, 1, (Index)m, (Index)nnz, NULL, NULL, vals, h)) {
+    /* one iterate as Ipopt drives it: new_x only on the first callback */
+    if (!eval_f((Index)n, Z, 1, &f, h) || !eval_grad_f((Index)n, Z, 0, grad, h) || !eval_g((Index)n, Z, 0, (Index)m, g, h) ||
+        !eval_jac_g((Index)n, Z, 0, (Index)m, (Index)nnz, iRow, jCol, NULL, h) ||
+        !eval_jac_g((Index)n, Z, 0, (Index)m, (Index)nnz, NULL, NULL, vals, h)) {
         fprintf(stderr, "evaluation failed: %s\n", qlnlp_last_error());
         return 2;
     }

@@ -98,7 +98,7 @@ int qlnlp_devices(qlnlp_handle h, int* devices, int cap, int* ndev);
 /* shard `shard` of `nshards` covers evaluations [lo, hi): contiguous and balanced, the first B % nshards shards hold
  * one extra evaluation */
 int qlnlp_shard_bounds(int64_t B, int nshards, int shard, int64_t* lo, int64_t* hi);
-/* tuning knobs: "host_chunk" (evaluations per pipeline stage of the host-pointer path, default 256), "host_threads"
+/* tuning knobs: "host_chunk" (evaluations per pipeline stage of the host-pointer path, default 512), "host_threads"
  * (row-builder threads per device, 0 = this handle's share of the CPUs the process may use), "pin_threads" (0/1),
  * "x_cache" (0/1: serve repeated single-evaluation callbacks at the same x from the last evaluation) */
 int qlnlp_set_option(qlnlp_handle h, const char* name, int64_t value);
@@ -172,6 +172,13 @@ typedef struct {
 } qlnlp_ragged_io;
 #define QLNLP_RAGGED_Z_PADDED 1
 int qlnlp_eval_ragged_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, const qlnlp_ragged_io* rg, void* stream);
+/* The whole mixed batch in ONE launch: problem i belongs to the class of handles[class_of[i]] (all handles on one
+ * device, same Jacobian pattern).  The B evaluations of the launch are the problems index[0..B) (or 0..B-1); a warp
+ * swaps class records when the class changes from one of its evaluations to the next, so order `index` by class
+ * (largest horizon first balances the tail).  class_of is a device array of int32; the handles must stay alive while
+ * launches that name them are in flight. */
+int qlnlp_eval_ragged_classes(const qlnlp_handle* handles, int nclasses, int64_t B, const qlnlp_batch_io* io,
+                              const qlnlp_ragged_io* rg, const int32_t* class_of, void* stream);
 
 /* One shard per device of a multi-device handle (or the single device of a plain one): B[i] evaluations on the
  * DEVICE pointers of io[i], which live on device i of the handle, enqueued on streams[i] (NULL array or entry = that
@@ -180,7 +187,7 @@ int qlnlp_eval_batch_device_multi(qlnlp_handle h, const int64_t* B, const qlnlp_
 int qlnlp_synchronize(qlnlp_handle h);
 
 /* All pointers are HOST pointers.  Copies Z (and x0/xf) to the device, evaluates, copies the requested outputs back,
- * and returns when they are in place.  Work is pipelined in chunks over three streams so copies overlap the kernel;
+ * and returns when they are in place.  Work is pipelined in chunks over four streams so copies overlap the kernel;
  * pinned (page-locked) host arrays make the copies asynchronous (qlnlp_host_pin).  For batches >= 64 only the
  * VALUE-DEPENDENT Jacobian entries cross PCIe (2,794 of the 32,161 SPARSE_BLOCK values at the default instance): a
  * persistent pool of host threads assembles the caller's rows from the constant image of the pattern (zeros, +-1)

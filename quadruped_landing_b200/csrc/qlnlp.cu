@@ -93,6 +93,16 @@ struct Registration {
     int64_t ld, rows;
 };
 
+// class table of a ragged launch (device copy of one QlRagClass per handle) + the launch geometry for its largest horizon
+struct RagTable {
+    ql::QlRagClass* d_classes = nullptr;
+    int ncls = 0;
+    QlClass layout;                    // the class with the largest N: sizes the shared-memory carve-up
+    bool fastdiv = false;
+    size_t smem[NJM] = {0, 0, 0, 0};
+    int blocks_per_sm[NJM] = {0, 0, 0, 0};
+};
+
 }  // namespace
 
 struct qlnlp_handle_s {
@@ -130,12 +140,15 @@ struct qlnlp_handle_s {
     unsigned* ticket_pool = nullptr;             // pre-zeroed counters (128 B apart) so that a launch needs no
     int ticket_pool_used = 0;                    // allocation: launches stay legal inside CUDA-graph capture
     std::string pci_bus_id;
+    size_t smem_per_sm = 0, smem_optin = 0;
+    uint64_t serial = 0;               // unique per handle ever created (addresses get reused)
+    std::map<std::vector<uint64_t>, RagTable> rag_tables;       // ragged launches led by this handle (key: the classes' serials)
 
     // host-pointer path: row plan of the handle's batch pattern, worker pool, registered output buffers
     std::unique_ptr<qlhost::RowPlan> plan;
     std::unique_ptr<qlhost::Pool> pool;
     std::vector<Registration> regs;
-    int64_t opt_host_chunk = 256;
+    int64_t opt_host_chunk = 512;
     int64_t opt_host_threads = 0;      // 0: this handle's share of the process's CPUs
     int64_t opt_pin_threads = 1;
     int64_t opt_x_cache = 1;
@@ -405,6 +418,17 @@ int ensure_pool(qlnlp_handle h)
     return QLNLP_OK;
 }
 
+int set_carveout(const void* fn, int resident_blocks, size_t smem_per_block, size_t smem_per_sm)
+{
+    static std::map<const void*, size_t> g_need;
+    size_t& need = g_need[fn];
+    need = std::max(need, (size_t)resident_blocks * (smem_per_block + 1024));
+    const int pct = (int)std::min<size_t>(100, need * 100 / std::max<size_t>(1, smem_per_sm) + 2);
+    if (!std::getenv("QLNLP_MAX_CARVEOUT"))
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    return QLNLP_OK;
+}
+
 int check_handle(qlnlp_handle h)
 {
     if (!h) return fail(QLNLP_EINVAL, "null handle");
@@ -430,6 +454,8 @@ int ensure_device(qlnlp_handle h)
         return fail(QLNLP_ENODEVICE, "device %d is sm_%d%d; this build targets sm_100a (B200) only", h->device, prop.major,
                     prop.minor);
     h->sm_count = prop.multiProcessorCount;
+    h->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
     char bus[32] = {0};
     if (cudaDeviceGetPCIBusId(bus, sizeof bus, h->device) == cudaSuccess) h->pci_bus_id = bus;
 
@@ -467,15 +493,7 @@ int ensure_device(qlnlp_handle h)
             // Shared memory the resident warps really need: whatever the SM has beyond that serves as L1 (the cost
             // table and the boundary states are re-read by every warp).  The attribute belongs to the FUNCTION, so it
             // only ever grows (handles of other horizons share it).
-            {
-                static std::map<const void*, size_t> g_need;
-                const int used = (wj == ql::JM_BLOCK && !env) ? std::min(nb, 6) : nb;      // see launch()
-                size_t& need = g_need[fn];
-                need = std::max(need, (size_t)used * (h->smem[wj] + 1024));
-                const int pct = (int)std::min<size_t>(100, need * 100 / (size_t)prop.sharedMemPerMultiprocessor + 2);
-                if (!std::getenv("QLNLP_MAX_CARVEOUT"))
-                    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-            }
+            if (int rc = set_carveout(fn, (wj == ql::JM_BLOCK && !env) ? std::min(nb, 6) : nb, h->smem[wj], h->smem_per_sm)) return rc;
         }
     }
     for (auto& ln : h->lanes) {
@@ -499,9 +517,10 @@ int ensure_device(qlnlp_handle h)
 }
 
 int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t stream, int jm_force = -1,
-           const qlnlp_ragged_io* rg = nullptr)
+           const qlnlp_ragged_io* rg = nullptr, const RagTable* table = nullptr, const int32_t* class_of = nullptr)
 {
     const QlClass& c = h->cls;
+    if (rg && !table) return fail(QLNLP_EINVAL, "internal: ragged launch without a class table");
     if (B < 0) return fail(QLNLP_EINVAL, "negative batch");
     if (B == 0) return QLNLP_OK;          // an empty shard is not an error (its pointers may be NULL)
     if (!io || !io->Z) return fail(QLNLP_EINVAL, "io->Z is required");
@@ -519,7 +538,9 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     if ((reinterpret_cast<uintptr_t>(io->Z) & 7) != 0) return fail(QLNLP_EINVAL, "Z must be 8-byte aligned");
 
     ql::Launch P;
-    P.c = c;
+    P.c = rg ? table->layout : c;
+    P.classes = rg ? table->d_classes : nullptr;
+    P.cls_of = rg ? reinterpret_cast<const int*>(class_of) : nullptr;
     P.rmb = h->rmb; P.rmf = h->rmf; P.rIb = h->rIb;
     P.cost = h->d_cost;
     P.npad = h->npad;
@@ -547,7 +568,9 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     // Resident warps per SM.  The SPARSE_BLOCK stream is store-bound and the memory system takes the output of a
     // few fast warps better than that of all 8 that fit (occupancy sweeps in profiles/r01_ablation.md, section 7):
     // 5 per SM, 6 for short batches that also want the cost/gradient.
-    int per_sm = h->blocks_per_sm[wj];
+    int per_sm = rg ? table->blocks_per_sm[wj] : h->blocks_per_sm[wj];
+    const size_t smem = rg ? table->smem[wj] : h->smem[wj];
+    const bool fast = rg ? table->fastdiv : h->fastdiv;
     if (wj == ql::JM_BLOCK && !std::getenv("QLNLP_BLOCKS_PER_SM")) {
         const bool want_cost = io->f || io->grad;
         const bool short_batch = B < 8 * (int64_t)h->sm_count * 6;
@@ -579,12 +602,69 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
     }
     P.ticket = it->second;
     void* args[] = {&P};
-    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj, h->fastdiv, rg != nullptr), dim3(grid), dim3(QL_LANES), args, h->smem[wj], stream));
+    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj, fast, rg != nullptr), dim3(grid), dim3(QL_LANES), args, smem, stream));
     h->last_launch[0] = grid;
     h->last_launch[1] = QL_LANES;
-    h->last_launch[2] = (int64_t)h->smem[wj];
+    h->last_launch[2] = (int64_t)smem;
     h->last_launch[3] = per_sm;
     h->last_launch[4] = h->sm_count;
+    return QLNLP_OK;
+}
+
+// The class table of a ragged launch over the handles `hs` (all on one device, already bound to it), cached in hs[0].
+int ragged_table(const qlnlp_handle* hs, int ncls, const RagTable** out)
+{
+    qlnlp_handle lead = hs[0];
+    std::vector<uint64_t> key((size_t)ncls);
+    for (int i = 0; i < ncls; ++i) key[(size_t)i] = hs[i]->serial;
+    auto it = lead->rag_tables.find(key);
+    if (it != lead->rag_tables.end()) { *out = &it->second; return QLNLP_OK; }
+    RagTable t;
+    t.ncls = ncls;
+    t.fastdiv = true;
+    t.layout = hs[0]->cls;
+    std::vector<ql::QlRagClass> host((size_t)ncls);
+    for (int i = 0; i < ncls; ++i) {
+        qlnlp_handle h = hs[i];
+        ql::QlRagClass& r = host[(size_t)i];
+        std::memset(&r, 0, sizeof r);
+        r.c = h->cls;
+        r.rmb = h->rmb; r.rmf = h->rmf; r.rIb = h->rIb;
+        r.cost = h->d_cost;
+        r.x0_def = h->d_x0xf;
+        r.xf_def = h->d_x0xf + QL_NX;
+        r.segs = h->d_segs;
+        r.seg_begin = h->d_seg_begin;
+        r.npad = h->npad;
+        r.nseg = (int)h->segs.size();
+        t.fastdiv = t.fastdiv && h->fastdiv;
+        if (h->cls.N > t.layout.N) t.layout = h->cls;
+    }
+    // device records are QL_RAGCLASS_BYTES apart (the kernel copies whole slots)
+    std::vector<unsigned char> packed((size_t)ncls * QL_RAGCLASS_BYTES, 0);
+    for (int i = 0; i < ncls; ++i) std::memcpy(packed.data() + (size_t)i * QL_RAGCLASS_BYTES, &host[(size_t)i], sizeof(ql::QlRagClass));
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, packed.size()));
+    CUDA_TRY(cudaMemcpy(d, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());
+    t.d_classes = static_cast<ql::QlRagClass*>(d);
+    for (int wj = 0; wj < NJM; ++wj) {
+        if (wj == ql::JM_VALS) continue;
+        t.smem[wj] = ql::smem_bytes(t.layout.N, wj);
+        if (t.smem[wj] > lead->smem_optin) return fail(QLNLP_EINVAL, "N=%d needs %zu B of shared memory per warp", t.layout.N, t.smem[wj]);
+        const void* fn = kernel_fn(wj, t.fastdiv, true);
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, t.smem[wj]));
+        if (nb < 1) return fail(QLNLP_ECUDA, "kernel does not fit on an SM");
+        const char* env = std::getenv("QLNLP_BLOCKS_PER_SM");
+        if (env) {
+            const int cap = std::atoi(env);
+            if (cap >= 1 && cap < nb) nb = cap;
+        }
+        t.blocks_per_sm[wj] = nb;
+        if (int rc = set_carveout(fn, (wj == ql::JM_BLOCK && !env) ? std::min(nb, 6) : nb, t.smem[wj], lead->smem_per_sm)) return rc;
+    }
+    *out = &lead->rag_tables.emplace(key, t).first->second;
     return QLNLP_OK;
 }
 
@@ -928,6 +1008,7 @@ void destroy_device_state(qlnlp_handle h)
     if (h->one.stream) cudaStreamDestroy(h->one.stream);
     if (h->one.hx) cudaFreeHost(h->one.hx);
     cudaFree(h->one.dx); cudaFree(h->one.dout);
+    for (auto& kv : h->rag_tables) cudaFree(kv.second.d_classes);
     cudaFree(h->ticket_pool);
     cudaFree(h->d_cost); cudaFree(h->d_x0xf); cudaFree(h->d_segs); cudaFree(h->d_seg_begin);
     cudaFree(h->d_dense_lin); cudaFree(h->d_dense);
@@ -937,6 +1018,8 @@ int create_one(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_hand
 {
     qlnlp_handle h = new (std::nothrow) qlnlp_handle_s();
     if (!h) return fail(QLNLP_ENOMEM, "out of host memory");
+    static std::atomic<uint64_t> g_serial{0};
+    h->serial = ++g_serial;
     ql_class_init(&h->cls, (int)d->N, (int)d->k_trans, (int)d->init_mode, d->model.g, d->model.mb, d->model.mf, d->model.lb);
     ql_class_finish(&h->cls);
     h->device = device;
@@ -1166,7 +1249,30 @@ int qlnlp_eval_ragged_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io
     if (B == 0) return QLNLP_OK;
     DeviceGuard guard(h->device);
     if (int rc = ensure_device(h)) return rc;
-    return launch(h, B, io, static_cast<cudaStream_t>(stream), -1, rg);
+    const RagTable* table = nullptr;
+    if (int rc = ragged_table(&h, 1, &table)) return rc;
+    return launch(h, B, io, static_cast<cudaStream_t>(stream), -1, rg, table, nullptr);
+}
+
+int qlnlp_eval_ragged_classes(const qlnlp_handle* hs, int ncls, int64_t B, const qlnlp_batch_io* io,
+                              const qlnlp_ragged_io* rg, const int32_t* class_of, void* stream)
+{
+    if (!hs || ncls < 1 || ncls > 4096) return fail(QLNLP_EINVAL, "bad class list");
+    if (!rg) return fail(QLNLP_EINVAL, "null ragged descriptor");
+    if (ncls > 1 && !class_of) return fail(QLNLP_EINVAL, "class_of is required with more than one class");
+    for (int i = 0; i < ncls; ++i) {
+        if (int rc = check_handle(hs[i])) return rc;
+        if (!hs[i]->subs.empty()) return fail(QLNLP_EINVAL, "multi-device handle: ragged launches take single-device handles");
+        if (hs[i]->device != hs[0]->device) return fail(QLNLP_EINVAL, "the classes of a ragged launch must share one device");
+        if (batch_jm(hs[i]) != batch_jm(hs[0])) return fail(QLNLP_EINVAL, "the classes of a ragged launch must share one Jacobian pattern");
+    }
+    if (B == 0) return QLNLP_OK;
+    DeviceGuard guard(hs[0]->device);
+    for (int i = 0; i < ncls; ++i)
+        if (int rc = ensure_device(hs[i])) return rc;
+    const RagTable* table = nullptr;
+    if (int rc = ragged_table(hs, ncls, &table)) return rc;
+    return launch(hs[0], B, io, static_cast<cudaStream_t>(stream), -1, rg, table, class_of);
 }
 
 int qlnlp_eval_batch_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)

@@ -150,8 +150,23 @@ namespace ql {
 
 #define QL_NJ_MAX (QL_NJ_MODE1 > QL_NJ_MODE3 ? QL_NJ_MODE1 : QL_NJ_MODE3)
 
-struct Launch {
+// One (N, k_trans, init_mode, model, cost table) class of a RAGGED launch: what `Launch` carries for a plain one.
+struct QlRagClass {
     QlClass c;
+    double rmb, rmf, rIb;
+    const double* cost;
+    const double* x0_def;
+    const double* xf_def;
+    const QlSeg* segs;
+    const int* seg_begin;
+    int npad;
+    int nseg;
+};
+#define QL_RAGCLASS_BYTES 192
+static_assert(sizeof(QlRagClass) <= QL_RAGCLASS_BYTES && QL_RAGCLASS_BYTES % 16 == 0, "QlRagClass does not fit its shared-memory slot");
+
+struct Launch {
+    QlClass c;                 // RAGGED launches: only c.N matters here (the LARGEST horizon, for the shared-memory layout)
     double rmb, rmf, rIb;      // RN(1/mb), RN(1/mf), RN(1/Ib)
     const double* cost;        // [QL_NCOST][npad] field-major: Q 0-14, q 15-29, R 30-34, r 35-39, c 40
     int npad;
@@ -174,6 +189,8 @@ struct Launch {
     const long long* z_off;
     const long long* g_off;
     const long long* j_off;
+    const QlRagClass* classes; // RAGGED: per-class records; problem i belongs to class cls_of[i] (class 0 when cls_of is null)
+    const int* cls_of;
     unsigned* ticket;          // [0] next evaluation to hand out, [1] CTAs that have finished (both 0 between launches)
     int bulk;                  // 1: jac rows are 16 B aligned -> TMA bulk stores
     int zbulk;                 // 1: Z rows are 16 B aligned and ldz > n_nlp -> one TMA bulk load per vector
@@ -195,7 +212,7 @@ __host__ __device__ inline size_t smem_jregion_bytes(int N, int jm)
 }
 __host__ __device__ inline size_t smem_bytes(int N, int jm)
 {
-    return sizeof(double) * (size_t)(zbuf_len(N) + QL_FBUF) + smem_jregion_bytes(N, jm);
+    return sizeof(double) * (size_t)(zbuf_len(N) + QL_FBUF) + QL_RAGCLASS_BYTES + smem_jregion_bytes(N, jm);
 }
 
 // Start fetching a decision vector into shared memory.  zbulk: one TMA bulk load of n+1 doubles (n is odd, the
@@ -218,13 +235,18 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
 {
     constexpr bool WITH_JAC = JM != JM_NONE;
     extern __shared__ __align__(16) double smem[];
-    const QlClass& c = P.c;
     const int lane = threadIdx.x;
 
+    // layout (RAGGED: sized for the largest horizon of the launch, P.c.N)
     double* const zbuf = smem;
-    const unsigned mbar = smem_addr(zbuf + zbuf_len(c.N) - 1);      // 8-byte mbarrier behind the staged vector
-    double* const fbuf = zbuf + zbuf_len(c.N);
-    double* const jb = fbuf + QL_FBUF;
+    const unsigned mbar = smem_addr(zbuf + zbuf_len(P.c.N) - 1);      // 8-byte mbarrier behind the staged vector
+    double* const fbuf = zbuf + zbuf_len(P.c.N);
+    QlRagClass* const rc = reinterpret_cast<QlRagClass*>(fbuf + QL_FBUF);       // RAGGED: the class being evaluated
+    double* const jb = fbuf + QL_FBUF + QL_RAGCLASS_BYTES / 8;
+    // RAGGED launches mix classes: the record of the current evaluation's class lives in shared memory and is swapped
+    // when the class changes (the caller orders the problems by class, so that happens a handful of times per warp)
+    const QlClass& c = RAGGED ? rc->c : P.c;
+    int cur_cls = -1;
     QlSeg* const plan = reinterpret_cast<QlSeg*>(jb + 2 * QL_JBUF);
     const unsigned zaddr = smem_addr(zbuf);
     const unsigned jaddr = smem_addr(jb);
@@ -235,8 +257,17 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
     // cost coefficients: from shared memory ([41][N], copied once per CTA) when the launch has room for it, else
     // from the field-major global table (L2)
     Consts<FASTDIV> K;
-    K.g = c.g; K.mb = c.mb; K.mf = c.mf; K.Ib = c.Ib; K.rmb = P.rmb; K.rmf = P.rmf; K.rIb = P.rIb;
-    const bool first_is_y1 = (c.init_mode == 1);    // contact-first reads y1 (mode 1) or y2 (mode 2)
+    if (!RAGGED) { K.g = c.g; K.mb = c.mb; K.mf = c.mf; K.Ib = c.Ib; K.rmb = P.rmb; K.rmf = P.rmf; K.rIb = P.rIb; }
+    const double* cost = P.cost;
+    const double* x0_def = P.x0_def;
+    const double* xf_def = P.xf_def;
+    const int* seg_begin = P.seg_begin;
+    int npad = P.npad;
+    auto cls_of = [&](long long t) -> int {           // class of the t-th evaluation of a RAGGED launch
+        const long long i = P.index ? __ldg(P.index + t) : t;
+        return P.cls_of ? __ldg(P.cls_of + i) : 0;
+    };
+    auto n_of = [&](long long t) -> int { return RAGGED ? __ldg(&P.classes[cls_of(t)].c.n_nlp) : P.c.n_nlp; };
 
     const bool zbulk = P.zbulk != 0;      // ragged launches: only when the caller guarantees aligned, padded Z rows
     auto zrow_of = [&](long long t) -> const double* {
@@ -260,8 +291,8 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
     };
     long long b = take();
     long long nb = P.B;
-    if (b < P.B) stage_z(zrow_of(b), zaddr, mbar, c.n_nlp, lane, zbulk);
-    if (JM == JM_BLOCK) {
+    if (b < P.B) stage_z(zrow_of(b), zaddr, mbar, n_of(b), lane, zbulk);
+    if (JM == JM_BLOCK && !RAGGED) {
         // the segment plan lives in shared memory: one 16-byte record per segment
         const int4* src = reinterpret_cast<const int4*>(P.segs);
         int4* dst = reinterpret_cast<int4*>(plan);
@@ -277,9 +308,37 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
         // round trip is hidden behind this evaluation (the SPARSE_BLOCK kernel has no register to spare for it)
         if (JM != JM_BLOCK) {
             nb = take();
-            if (zbulk && nb < P.B && lane == 0) prefetch_l2(zrow_of(nb), 8u * (unsigned)(c.n_nlp + 1));
+#ifndef QL_NO_L2_PREFETCH
+            // (measured: +13 % with the cost/gradient part in the evaluation, -17 % for the short g-only evaluation,
+            // where the prefetch is still in flight when the load itself is issued; profiles/r02_kernel_ab.md)
+            if (zbulk && (P.f || P.grad) && nb < P.B && lane == 0) prefetch_l2(zrow_of(nb), 8u * (unsigned)(n_of(nb) + 1));
+#endif
         }
         const long long pi = (RAGGED && P.index) ? __ldg(P.index + b) : b;      // problem number (f, x0, xf, offsets)
+        if (RAGGED) {
+            const int cid = P.cls_of ? __ldg(P.cls_of + pi) : 0;
+            if (cid != cur_cls) {
+                // swap the class record (and, for SPARSE_BLOCK, the segment plan) in; the staging buffers' constant
+                // images belong to the old class
+                if (P.bulk && lane == 0) bulk_wait_read<0>();      // stores in flight still read the staging buffers
+                __syncwarp();
+                const int4* src = reinterpret_cast<const int4*>(P.classes + cid);
+                int4* dst = reinterpret_cast<int4*>(rc);
+                if (lane < QL_RAGCLASS_BYTES / 16) dst[lane] = __ldg(src + lane);
+                __syncwarp();
+                if (JM == JM_BLOCK) {
+                    const int4* ps = reinterpret_cast<const int4*>(rc->segs);
+                    int4* pd = reinterpret_cast<int4*>(plan);
+                    for (int i = lane; i < rc->nseg; i += QL_LANES) pd[i] = __ldg(ps + i);
+                    __syncwarp();
+                }
+                tmpl0 = tmpl1 = -1;
+                cur_cls = cid;
+            }
+            K.g = c.g; K.mb = c.mb; K.mf = c.mf; K.Ib = c.Ib; K.rmb = rc->rmb; K.rmf = rc->rmf; K.rIb = rc->rIb;
+            cost = rc->cost; x0_def = rc->x0_def; xf_def = rc->xf_def; seg_begin = rc->seg_begin; npad = rc->npad;
+        }
+        const bool first_is_y1 = (c.init_mode == 1);    // contact-first reads y1 (mode 1) or y2 (mode 2)
         double* const grow = P.g ? P.g + (RAGGED ? __ldg(P.g_off + pi) : b * P.ldg) : nullptr;
         double* const gradrow = P.grad ? P.grad + (RAGGED ? __ldg(P.z_off + pi) : b * P.ldgrad) : nullptr;
         double* const jrow = WITH_JAC ? P.jac + (RAGGED ? __ldg(P.j_off + pi) : b * P.ldjac) : nullptr;
@@ -288,8 +347,8 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
 
         if (grow) {
             // boundary rows (constraints.jl:149-150) straight from the staged vector, one lane per row
-            const double* x0 = P.x0 ? P.x0 + pi * QL_NX : P.x0_def;
-            const double* xf = P.xf ? P.xf + pi * QL_NX : P.xf_def;
+            const double* x0 = P.x0 ? P.x0 + pi * QL_NX : x0_def;
+            const double* xf = P.xf ? P.xf + pi * QL_NX : xf_def;
             if (lane < QL_NX) grow[lane] = __dsub_rn(zbuf[lane], __ldg(x0 + lane));
             if (lane < QL_NX - 1) grow[c.c_term + lane] = __dsub_rn(zbuf[(c.N - 1) * QL_NZK + lane], __ldg(xf + lane));
             __syncwarp();
@@ -323,8 +382,8 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
             // ---- 2. cost and gradient (costs.jl:6-34, quadratic_cost.jl:44-52); gradient in place over Z
             double lane_term = 0.0;
             if (act && (P.f || gradrow)) {
-                const double* ct = P.cost + (k - 1);
-                const int np = P.npad;
+                const double* ct = cost + (k - 1);
+                const int np = npad;
                 double cq[QL_NCOST];                // all loads first: their latency overlaps
 #pragma unroll
                 for (int i = 0; i < QL_NCOST; ++i) cq[i] = __ldg(ct + i * np);
@@ -462,7 +521,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
             if (p == c.npass - 1) {
                 // zbuf is dead: prefetch the next decision vector while the Jacobian values stream out
                 if (JM == JM_BLOCK) nb = take();
-                if (nb < P.B) stage_z(zrow_of(nb), zaddr, mbar, c.n_nlp, lane, zbulk);
+                if (nb < P.B) stage_z(zrow_of(nb), zaddr, mbar, n_of(nb), lane, zbulk);
             }
 
             // ---- 5'. SPARSE_TRUE: every lane writes its whole run; the pass leaves as two bulk stores of 16 knots
@@ -505,7 +564,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
             if (JM == JM_BLOCK) {
                 const int roff = act ? ql_run_off(c, k) : 0;
                 const int e4 = ql_e4(c, k), e6 = ql_e6(c, k), fc = ql_fc(c, k);
-                const int sb = __ldg(P.seg_begin + p), se = __ldg(P.seg_begin + p + 1);
+                const int sb = __ldg(seg_begin + p), se = __ldg(seg_begin + p + 1);
                 for (int s = sb; s < se; ++s) {
                     const int4 rec = *reinterpret_cast<const int4*>(plan + s);
                     const int start = rec.x, end = rec.y;

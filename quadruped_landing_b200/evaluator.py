@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     "qlnlp_create_multi", "qlnlp_devices", "qlnlp_shard_bounds", "qlnlp_set_option", "qlnlp_eval_all",
     "qlnlp_eval_batch_device_multi", "qlnlp_synchronize", "qlnlp_host_output_register", "qlnlp_host_output_unregister",
     "qlnlp_host_pin", "qlnlp_host_unpin", "qlnlp_host_path_info", "qlnlp_host_alloc", "qlnlp_host_free",
+    "qlnlp_eval_ragged_classes",
 )
 _DEBUG_SYMBOLS = ("qlnlp_debug_segments", "qlnlp_debug_vals_map", "qlnlp_debug_build_rows", "qlnlp_debug_host_times")
 
@@ -101,6 +102,7 @@ def load_library(rebuild_if_stale: bool = True):
     L.qlnlp_eval_batch_device.argtypes = [vp, C.c_int64, C.POINTER(_BatchIO), vp]
     L.qlnlp_eval_ragged_device.argtypes = [vp, C.c_int64, C.POINTER(_BatchIO), C.POINTER(_RaggedIO), vp]
     L.qlnlp_eval_batch_host.argtypes = [vp, C.c_int64, C.POINTER(_BatchIO)]
+    L.qlnlp_eval_ragged_classes.argtypes = [C.POINTER(vp), C.c_int, C.c_int64, C.POINTER(_BatchIO), C.POINTER(_RaggedIO), vp, vp]
     L.qlnlp_launch_info.argtypes = [vp, i64p]
     L.qlnlp_debug_segments.argtypes = [vp, vp, C.c_int64, i64p]
     L.qlnlp_debug_vals_map.argtypes = [vp, vp, C.c_int64, i64p]
@@ -493,6 +495,36 @@ class HybridNLP:
         dev = flat["Z"].device
         s = torch.cuda.current_stream(dev) if stream is None else stream
         _check(load_library().qlnlp_eval_ragged_device(self._h, B, C.byref(io), C.byref(rg), C.c_void_p(s.cuda_stream)))
+
+    @staticmethod
+    def eval_ragged_classes(nlps: Sequence["HybridNLP"], index, class_of, flat: Dict[str, "object"],
+                            offsets: Dict[str, "object"], *, x0=None, xf=None, stream=None, z_padded: bool = False) -> None:
+        """The whole mixed batch in ONE launch (``qlnlp_eval_ragged_classes``): problem ``i`` belongs to
+        ``nlps[class_of[i]]`` (``class_of``: int32 CUDA tensor over all problems); the launch evaluates the problems
+        ``index`` (int64 CUDA tensor; order it by class).  Other arguments as in ``eval_ragged``."""
+        import torch
+
+        B = int(index.shape[0])
+        io = _BatchIO()
+        io.Z = flat["Z"].data_ptr()
+        for name in ("f", "grad", "g", "jac"):
+            if flat.get(name) is not None:
+                setattr(io, name, flat[name].data_ptr())
+        if x0 is not None:
+            io.x0 = x0.data_ptr()
+        if xf is not None:
+            io.xf = xf.data_ptr()
+        rg = _RaggedIO(index.data_ptr(), offsets["z_off"].data_ptr(),
+                       offsets["g_off"].data_ptr() if flat.get("g") is not None else None,
+                       offsets["j_off"].data_ptr() if flat.get("jac") is not None else None,
+                       1 if z_padded else 0)
+        hs = (C.c_void_p * len(nlps))(*[n._h.value for n in nlps])
+        dev = flat["Z"].device
+        s = torch.cuda.current_stream(dev) if stream is None else stream
+        if class_of.dtype != torch.int32:
+            raise ValueError("class_of must be an int32 CUDA tensor")
+        _check(load_library().qlnlp_eval_ragged_classes(hs, len(nlps), B, C.byref(io), C.byref(rg),
+                                                        C.c_void_p(class_of.data_ptr()), C.c_void_p(s.cuda_stream)))
 
     def eval_batch_host(self, Z: np.ndarray, *, x0: Optional[np.ndarray] = None, xf: Optional[np.ndarray] = None,
                         want: Sequence[str] = ("f", "grad", "g", "jac"),

@@ -1,9 +1,10 @@
 """Ragged batches: problems of mixed horizon / contact schedule in one call.
 
 The reference has a single problem size per `HybridNLP`; "varying horizon" sweeps therefore mix several
-(N, k_trans, init_mode) classes.  Each class gets its own handle (its own segment plan and templates) and is
-evaluated with one fused launch on its own CUDA stream, so classes overlap on the GPU.  Inputs and outputs
-are flat arrays with offset tables, the layout C4 asks for.
+(N, k_trans, init_mode) classes.  Each class gets its own handle (its own segment plan and cost tables); the
+whole mixed batch is evaluated by ONE fused launch (`qlnlp_eval_ragged_classes`): problems are handed out
+ordered by class, largest horizon first, and a warp swaps class records when the class changes.  Inputs and
+outputs are flat arrays with offset tables, the layout C4 asks for.
 """
 from __future__ import annotations
 
@@ -27,7 +28,8 @@ class RaggedEvaluator:
         self.nnz = np.array([e.nnz_block for e in self.nlps], dtype=np.int64)
         self._streams = None
         self._plan = None
-        self.launches_per_eval = len(self.nlps)        # one fused launch per class
+        self.launches_per_eval = 1                     # one fused launch for the whole mixed batch
+        self.single_launch = True                      # False: one launch per class on its own stream (the older path)
 
     def offsets(self, class_of: np.ndarray) -> Dict[str, np.ndarray]:
         """Row starts (in doubles): problem b owns Z[z_off[b] : z_off[b] + n_b], g[g_off[b] : ...], jac[j_off[b] : ...].
@@ -60,7 +62,16 @@ class RaggedEvaluator:
         for c in range(len(self.nlps)):
             idx = np.nonzero(class_of == c)[0]
             index.append(torch.from_numpy(idx).to(dev) if idx.size else None)
-        return RaggedPlan(class_of.copy(), off, doff, index)
+        # single launch: all problems, ordered by class, largest horizon first (the long evaluations start first)
+        order = np.argsort(-np.array([e.N for e in self.nlps])[class_of], kind="stable")
+        by_class = sorted(range(len(self.nlps)), key=lambda c: -self.nlps[c].N)
+        rank_of = np.empty(len(self.nlps), dtype=np.int64)
+        rank_of[by_class] = np.arange(len(self.nlps))
+        order = np.argsort(rank_of[class_of], kind="stable")
+        plan = RaggedPlan(class_of.copy(), off, doff, index)
+        plan.order = torch.from_numpy(order.astype(np.int64)).to(dev)
+        plan.dclass = torch.from_numpy(class_of.astype(np.int32)).to(dev)
+        return plan
 
     def eval(self, class_of, Z_flat, want=("f", "grad", "g", "jac"), out=None):
         """``Z_flat``: 1-D float64 CUDA tensor holding the decision vectors back to back (see ``offsets``);
@@ -93,13 +104,16 @@ class RaggedEvaluator:
                     t = torch.empty(sizes[name], dtype=torch.float64, device=dev)
                 flat[name] = t
         cur = torch.cuda.current_stream(dev)
-        for c, nlp in enumerate(self.nlps):
-            if plan.index[c] is None:
-                continue
-            s = self._streams[c]
-            s.wait_stream(cur)
-            nlp.eval_ragged(plan.index[c], flat, plan.doff, stream=s, z_padded=True)
-            cur.wait_stream(s)
+        if self.single_launch:
+            HybridNLP.eval_ragged_classes(self.nlps, plan.order, plan.dclass, flat, plan.doff, z_padded=True)
+        else:
+            for c, nlp in enumerate(self.nlps):
+                if plan.index[c] is None:
+                    continue
+                s = self._streams[c]
+                s.wait_stream(cur)
+                nlp.eval_ragged(plan.index[c], flat, plan.doff, stream=s, z_padded=True)
+                cur.wait_stream(s)
         res = {k: v for k, v in flat.items() if k != "Z"}
         res.update(off)
         self._keep = plan                  # alive until the next call: the launches are asynchronous

@@ -265,6 +265,46 @@ def test_c4_ragged_batch_of_mixed_horizons():
         assert_same_bits(ev.nlps[c], got, ref, f"problem {b} class {classes[c]}: ")
 
 
+def test_ragged_single_launch_equals_one_launch_per_class():
+    """qlnlp_eval_ragged_classes (one launch, class records swapped per warp) against qlnlp_eval_ragged_device per class:
+    identical bits, for a batch whose classes come in random order, including classes with a single problem."""
+    classes = [(31, 11, 1), (2, 1, 2), (61, 21, 2), (121, 41, 1), (33, 33, 2), (65, 2, 1)]
+    probs = [ql.build_problem(N=N, k_trans=kt, init_mode=im) for N, kt, im in classes]
+    ev = ql.RaggedEvaluator(probs)
+    rng = np.random.default_rng(11)
+    B = 777
+    class_of = rng.integers(0, len(classes), size=B)
+    class_of[5] = 1
+    guesses = [ql.initial_guess(p) if p.k_trans > 1 else np.zeros(p.n_nlp) for p in probs]
+    vecs = []
+    for c in class_of:
+        v = guesses[c] + 1e-2 * rng.standard_normal(probs[c].n_nlp)
+        v[19::20] = np.clip(v[19::20], 1e-3, 2e-2)
+        vecs.append(v)
+    Zd = torch.from_numpy(ev.pack(class_of, vecs)).cuda()
+    ev.single_launch = True
+    one = {k: v.clone() for k, v in ev.eval(class_of, Zd).items() if isinstance(v, torch.Tensor)}
+    torch.cuda.synchronize()
+    assert ev.nlps[0].launch_info()["blocks"] > 0
+    ev.single_launch = False
+    per = ev.eval(class_of, Zd)
+    torch.cuda.synchronize()
+    off = ev.offsets(class_of)
+    for b in range(B):          # compare the rows themselves (the padding between rows is never written)
+        e = ev.nlps[class_of[b]]
+        for k, o, w in (("grad", "z_off", e.n_nlp), ("g", "g_off", e.m_nlp), ("jac", "j_off", e.nnz_block)):
+            lo = int(off[o][b])
+            assert torch.equal(one[k][lo:lo + w], per[k][lo:lo + w]), (b, k)
+    assert torch.equal(one["f"], per["f"])
+    # partial outputs through the single launch
+    ev.single_launch = True
+    only = ev.eval(class_of, Zd, want=("g",))
+    torch.cuda.synchronize()
+    for b in range(0, B, 50):
+        lo, w = int(off["g_off"][b]), ev.nlps[class_of[b]].m_nlp
+        assert torch.equal(only["g"][lo:lo + w], per["g"][lo:lo + w])
+
+
 def test_c5_sized_shard_131072_per_gpu():
     """2^20 trajectories over 8 GPUs = 131,072 per GPU (33.7 GB of Jacobian values).  One shard
     is evaluated here; the result must not depend on the position in the batch, and a sample matches the oracle."""

@@ -21,15 +21,19 @@ for pattern in ("block", "true"):
     for reg in (False, True):
         if reg:
             t0 = time.perf_counter(); nlp.register_host_output(hout["jac"]); treg = time.perf_counter() - t0
-        for chunk in (128, 256, 512):
+        for chunk in [int(x) for x in os.environ.get('CHUNKS', '128,256,512').split(',')]:
             nlp.set_option("host_chunk", chunk)
             for _ in range(3):
                 nlp.eval_batch_host(Zp, out=hout)
             n = 15
-            t0 = time.perf_counter()
+            per = []
             for _ in range(n):
+                t0 = time.perf_counter()
                 nlp.eval_batch_host(Zp, out=hout)
-            dt = (time.perf_counter() - t0) / n
+                per.append(time.perf_counter() - t0)
+            dt = sum(per) / n
+            if os.environ.get("PER_CALL"):
+                print("      calls ms: " + " ".join(f"{x * 1e3:.1f}" for x in per))
             info = nlp.host_path_info()
             tt = nlp._debug_host_times()
             if not hasattr(nlp, "_tt"): nlp._tt = {k: 0.0 for k in tt}
