@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (read here, on the CPU box) into profiles/<name>.md + traffic.json.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_eval_kernel [--traffic]
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r02_eval_kernel_block [--traffic] [--what "command that was profiled"]
 """
 import csv
 import io
@@ -33,11 +33,13 @@ def to_bytes(v, unit):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
+    what = sys.argv[sys.argv.index("--what") + 1] if "--what" in sys.argv else \
+        "bench.py --steps 3 --warmup 3 --no-extras --no-cpu (B=4096 full evaluation per launch)"
     raw = list(csv.reader(io.StringIO(ncu(rep, "--page", "raw", "--csv"))))
     hdr, units, launches = raw[0], raw[1], raw[2:]
     md = [f"# ncu summary of `{rep}`", "",
           "Captured with `ncu --set full --clock-control none --import-source on -k regex:eval_kernel` on a B200 "
-          "under `bench.py --steps 3 --warmup 3 --no-cpu --min-warmup-s 0` (B=4096 full evaluation per launch). "
+          f"under `{what}`. "
           "Times under ncu are cold-cache and serialised; use the SHARES and per-launch counters.", ""]
     traffic = []
     for n, r in enumerate(launches):
