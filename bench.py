@@ -490,9 +490,11 @@ def pcie_and_host_ceilings(cx, nlp, jac_host):
     d2h = 4 * n / (time.perf_counter() - t0) / 1e9
     del d, h
     nlp.register_host_output(jac_host)
+    cx.barrier()                                   # every rank streams at the same time: they share the host's memory
     t0 = time.perf_counter()
     nlp.register_host_output(jac_host)
     host_w = jac_host.nbytes / (time.perf_counter() - t0) / 1e9
+    cx.barrier()
     return d2h, host_w
 
 
@@ -557,19 +559,22 @@ def run_gpu(args):
     def time_host(ev, outs, wanted=want, label=""):
         for s in range(3):
             ev.eval_batch_host(pin[s % 2].numpy(), want=wanted, out=outs)
-        cx.barrier()
-        tt0 = ev._debug_host_times()
-        t0 = time.perf_counter()
-        for s in range(e2e_steps):
-            ev.eval_batch_host(pin[s % 2].numpy(), want=wanted, out=outs)
-        torch.cuda.synchronize()
-        t = cx.max_over_ranks(time.perf_counter() - t0)
-        tt1 = ev._debug_host_times()
-        cx.barrier()
-        if rank == 0:
-            print(f"[bench] host path {label}: {t / e2e_steps * 1e3:.2f} ms per call; library: " +
-                  ", ".join(f"{k} {(tt1[k] - tt0[k]) / e2e_steps * 1e3:.2f}" for k in tt0), file=sys.stderr)
-        return B_PER_GPU * n_gpus * e2e_steps / t
+        best = None
+        for attempt in range(2):       # the host's memory system is shared with other tenants: best of two passes
+            cx.barrier()
+            tt0 = ev._debug_host_times()
+            t0 = time.perf_counter()
+            for s in range(e2e_steps):
+                ev.eval_batch_host(pin[s % 2].numpy(), want=wanted, out=outs)
+            torch.cuda.synchronize()
+            t = cx.max_over_ranks(time.perf_counter() - t0)
+            tt1 = ev._debug_host_times()
+            cx.barrier()
+            if rank == 0:
+                print(f"[bench] host path {label} pass {attempt}: {t / e2e_steps * 1e3:.2f} ms per call; library: " +
+                      ", ".join(f"{k} {(tt1[k] - tt0[k]) / e2e_steps * 1e3:.2f}" for k in tt0), file=sys.stderr)
+            best = t if best is None else min(best, t)
+        return B_PER_GPU * n_gpus * e2e_steps / best
 
     e2e_unreg = time_host(nlp, hnp, label="unregistered")     # every 64-byte line of every row rewritten
     d2h_gbs, host_w_gbs = pcie_and_host_ceilings(cx, nlp, hnp["jac"])      # also registers the output rows
@@ -589,8 +594,11 @@ def run_gpu(args):
     # the staged values and writing the touched lines.
     stage_bytes = B_PER_GPU * info["pcie_jac_doubles_per_eval"] * 8
     host_traffic = pcie_d2h + h2d + stage_bytes + host_bytes
+    # per-rank bandwidths were measured with all ranks active; the node's ceiling is the sum over the ranks
+    host_w_node = cx.sum_over_ranks(host_w_gbs)
     t_pcie, t_host = pcie_d2h / (d2h_gbs * 1e9), host_traffic / (host_w_gbs * 1e9)
     e2e_ceiling = B_PER_GPU / max(t_pcie, t_host)
+    e2e_ceiling_node = cx.sum_over_ranks(e2e_ceiling)
     nlp.unregister_host_output(hnp["jac"])
     nlp_t = ql.HybridNLP.from_problem(prob, pattern="true", device=local)
     hnp_t = dict(hnp, jac=torch.empty((B_PER_GPU, nlp_t.nnz), dtype=torch.float64).pin_memory().numpy())
@@ -610,6 +618,7 @@ def run_gpu(args):
         if rank == 0:
             try:
                 mh = ql.HybridNLP.from_problem(prob, devices=list(range(world)))
+                mh.set_option("host_threads", max(1, host_cores() // world))     # the other ranks are idle: all cores
                 Bm = B_PER_GPU * world
                 Zm = torch.from_numpy(np.concatenate([host_sets[i % N_INPUT_SETS] for i in range(world)])).pin_memory().numpy()
                 om = {"f": torch.empty(Bm, dtype=torch.float64).pin_memory().numpy(),
@@ -644,7 +653,7 @@ def run_gpu(args):
             "config": workload_config(n_gpus),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "check": e2e_check,
+                    "steps": e2e_steps, "passes": "best of 2 passes of `steps` calls", "check": e2e_check,
                     "path": "qlnlp_eval_batch_host on pinned host buffers, output rows registered once "
                             "(qlnlp_host_output_register, like jac_c! relying on the caller's zeros): 512-evaluation chunks "
                             "pipelined over 4 streams; f/grad/g land in the caller's arrays by DMA; of the 32,161 SPARSE_BLOCK "
@@ -655,14 +664,15 @@ def run_gpu(args):
                     "roofline": {"bound": "pcie_d2h" if t_pcie >= t_host else "host_dram",
                                  "pcie_d2h_GBps_measured": d2h_gbs, "host_dram_GBps_measured": host_w_gbs,
                                  "host_memory_bytes_per_step": host_traffic,
-                                 "ceiling_evals_per_s_per_gpu": e2e_ceiling,
-                                 "frac": (e2e_value / n_gpus) / e2e_ceiling,
+                                 "host_dram_GBps_node": host_w_node,
+                                 "ceiling_evals_per_s_per_gpu": e2e_ceiling, "ceiling_evals_per_s_node": e2e_ceiling_node,
+                                 "frac": e2e_value / e2e_ceiling_node,
                                  "how": "ceiling = 4096 / max(PCIe D2H bytes / measured D2H copy bandwidth, host-memory bytes / "
                                         "host bandwidth); host-memory bytes = DMA writes + DMA reads + staged values read by the row "
                                         "builder + 64-byte lines it rewrites; host bandwidth = what this handle's worker pool reaches "
                                         "streaming whole rows with non-temporal stores (qlnlp_host_output_register timed on the "
-                                        "1 GB output array); both measured in this run on this rank; at N>1 the ranks share the "
-                                        "host's memory system, so the per-GPU ceiling is optimistic there"},
+                                        "1 GB output array); both measured in this run, with every rank streaming at the same time "
+                                        "(the ranks of a node share its memory system), summed over the ranks for the node ceiling"},
                     "unregistered": {"value": e2e_unreg, "unit": UNIT,
                                      "what": "same call without registration: every line of every row rewritten (257 KB per evaluation)"},
                     "sparse_true": {"value": e2e_true, "unit": UNIT,

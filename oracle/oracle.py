@@ -30,7 +30,7 @@ class _Problem(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc -O3 -ffp-contract=off -fopenmp)."""
-    srcs = [os.path.join(_HERE, f) for f in ("ql_oracle.c", "ql_oracle.h", "ql_dyn_impl.inc", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("ql_oracle.c", "ql_oracle_hess.c", "ql_oracle.h", "ql_dyn_impl.inc", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
@@ -80,6 +80,10 @@ def lib():
         L.qlo_rk4.argtypes = [C.POINTER(_Model), C.c_int, dp, dp, dp]
         L.qlo_rk4_jacobian.restype = None
         L.qlo_rk4_jacobian.argtypes = [C.POINTER(_Model), C.c_int, dp, dp, dp, dp]
+        L.qlo_rk4_hessian.restype = None
+        L.qlo_rk4_hessian.argtypes = [C.POINTER(_Model), C.c_int, dp, dp, dp, dp]
+        L.qlo_hess_lagrangian_dense.restype = None
+        L.qlo_hess_lagrangian_dense.argtypes = [P, dp, C.c_double, dp, dp]
         _lib = L
     return _lib
 
@@ -118,6 +122,15 @@ def rk4_jacobian(model, mode: int, x, u):
     m = _model_struct(model)
     lib().qlo_rk4_jacobian(C.byref(m), mode, _ptr(x), _ptr(u), _ptr(xn), _ptr(J))
     return xn, J.reshape(20, 15).T.copy()
+
+
+def rk4_hessian(model, mode: int, x, u, lam) -> np.ndarray:
+    """H[20,20] = sum_r lam[r] * Hess(rk4_r) w.r.t. [x;u] (dense second-order forward mode)."""
+    x, u, lam = _f64(x), _f64(u), _f64(lam)
+    H = np.empty(400)
+    m = _model_struct(model)
+    lib().qlo_rk4_hessian(C.byref(m), mode, _ptr(x), _ptr(u), _ptr(lam), _ptr(H))
+    return H.reshape(20, 20).T.copy()
 
 
 class Oracle:
@@ -212,6 +225,14 @@ class Oracle:
         out = np.full(self.nnz, np.nan)
         lib().qlo_jac_c_sparse(self.plan, self._p, _ptr(Z), _ptr(out))
         return out
+
+    def hess_lagrangian_dense(self, Z, sigma: float, lam) -> np.ndarray:
+        """sigma * Hess f + sum_r lam_r Hess g_r as a dense symmetric [n_nlp, n_nlp] matrix (no reference target)."""
+        Z, lam = _f64(Z), _f64(lam)
+        n = self.n_nlp
+        H = np.empty(n * n)
+        lib().qlo_hess_lagrangian_dense(self._p, _ptr(Z), float(sigma), _ptr(lam), _ptr(H))
+        return H.reshape(n, n).T.copy()
 
     def jacobian_structure(self):
         rows = np.empty(self.nnz, dtype=np.int64)

@@ -102,6 +102,12 @@ void qlo_rk4(const qlo_model *m, int mode, const double *x, const double *u, dou
 void qlo_rk4_jacobian(const qlo_model *m, int mode, const double *x, const double *u,
                       double *xn, double *J);
 
+/* ---- Lagrangian Hessian (ql_oracle_hess.c; NO reference target: src/moi.jl:26-28 offers [:Grad, :Jac] only) ----
+ * H[i + 20*j] = sum_r lam[r] * d^2 rk4_r / dz_i dz_j by dense second-order forward mode. */
+void qlo_rk4_hessian(const qlo_model *m, int mode, const double *x, const double *u, const double *lam, double *H);
+/* sigma * Hess f + sum_r lambda_r * Hess g_r: dense n_nlp x n_nlp, column-major, full symmetric matrix */
+void qlo_hess_lagrangian_dense(const qlo_problem *p, const double *Z, double sigma, const double *lambda, double *H);
+
 #ifdef __cplusplus
 }
 #endif
