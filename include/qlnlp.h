@@ -133,6 +133,22 @@ int qlnlp_eval_constraint_jacobian(qlnlp_handle h, const double* x, double* vals
 /* all four at once (any output may be NULL): what the callbacks above do at a new x            moi.jl:1-24 */
 int qlnlp_eval_all(qlnlp_handle h, const double* x, double* f, double* grad, double* g, double* vals);
 
+/* ---- Lagrangian Hessian: what MOI.eval_hessian_lagrangian / hessian_lagrangian_structure need to offer [:Hess] ----
+ * NOT in the reference: src/moi.jl:26-28 advertises [:Grad, :Jac] and Ipopt runs L-BFGS (src/main.ipynb:219).
+ *   H = sigma * Hess f(x) + sum_r lambda_r * Hess g_r(x)
+ * with f as eval_f computes it (costs.jl:6-16; its true second derivatives, d/dh of h*stagecost included) and g as
+ * eval_c! (constraints.jl:145-158; lambda in that order).  H is block diagonal, one 20x20 block per knot; the
+ * structure is the lower triangle restricted to the structural non-zeros of each knot's mode, 1-based (row, col),
+ * column-major (3,355 entries at the default instance). */
+int qlnlp_hessian_nnz(qlnlp_handle h, int64_t* nnz);
+int qlnlp_hessian_structure(qlnlp_handle h, int64_t* rows, int64_t* cols);
+/* one evaluation on HOST pointers: x[n_nlp], lambda[m_nlp] -> vals[nnz_hess] */
+int qlnlp_eval_hessian_lagrangian(qlnlp_handle h, const double* x, double sigma, const double* lambda, double* vals);
+/* B evaluations on DEVICE pointers: Z[B][ldz], sigma[B] (NULL: 1.0), lambda[B][ldlambda], H[B][ldh]; enqueued on
+ * `stream`, not synchronised.  H 16-byte aligned with even ldh takes the TMA store path. */
+int qlnlp_eval_hessian_batch_device(qlnlp_handle h, int64_t B, const double* Z, int64_t ldz, const double* sigma,
+                                    const double* lambda, int64_t ldlambda, double* H, int64_t ldh, void* stream);
+
 /* ---- batched evaluation (B independent decision vectors; no reference equivalent) -------- */
 typedef struct {
     const double* Z;   int64_t ldz;     /* [B][ldz],    ldz    >= n_nlp          (required).  With Z 16-byte aligned

@@ -128,6 +128,20 @@ function gpu_eval_all!(ev::GpuEvaluator, x, grad_f, g, vec)
     return f[]
 end
 
+# Lagrangian Hessian (NOT in the reference: src/moi.jl:26-28 offers [:Grad, :Jac]); used when install!(...; hessian=true)
+function gpu_hessian_lagrangian_structure(ev::GpuEvaluator)
+    nnz = Ref{Int64}(0)
+    check(ccall((:qlnlp_hessian_nnz, LIBQLNLP), Cint, (Ptr{Cvoid}, Ref{Int64}), ev.handle, nnz))
+    rows = Vector{Int64}(undef, nnz[]); cols = Vector{Int64}(undef, nnz[])
+    check(ccall((:qlnlp_hessian_structure, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), ev.handle, rows, cols))
+    return collect(zip(rows, cols))                                           # lower triangle, 1-based
+end
+function gpu_eval_hessian_lagrangian(ev::GpuEvaluator, H, x, sigma, mu)
+    check(ccall((:qlnlp_eval_hessian_lagrangian, LIBQLNLP), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+                ev.handle, x, sigma, mu, H))
+    return nothing
+end
+
 # constraint / variable bounds as the library restates them (src/nlp.jl:66-69, src/moi.jl:51-67); solve() keeps using
 # the reference's own prob.lb / prob.ub, these are for callers that build the bounds themselves
 function constraint_bounds(ev::GpuEvaluator)
@@ -172,15 +186,16 @@ evaluator(nlp) = get(HANDLES, nlp) do
 end
 
 """
-    install!(nlp; sparse=false, pattern=:block, device=0, devices=nothing, into=Main)
+    install!(nlp; sparse=false, pattern=:block, device=0, devices=nothing, hessian=false, into=Main)
 
 Make `nlp` (a `HybridNLP` of the reference) evaluate on the GPU.  Re-defines, in module `into` (where the reference's
 src/nlp.jl and src/moi.jl were included), the seven MOI methods of src/moi.jl:1-33 for `::HybridNLP`; afterwards
 `solve(Z0, nlp; c_tol=1e-3, tol=1e-3)` (src/main.ipynb:742-744, src/moi.jl:46-103) runs without any edit.
 Every `HybridNLP` handed to MOI after this call needs its own `install!`.
 """
-function install!(nlp; into::Module=Main, kwargs...)
+function install!(nlp; into::Module=Main, hessian::Bool=false, kwargs...)
     HANDLES[nlp] = GpuEvaluator(nlp; kwargs...)
+    feats = hessian ? [:Grad, :Jac, :Hess] : [:Grad, :Jac]
     Core.eval(into, quote
         $MOI.eval_objective(prob::HybridNLP, x) =
             $gpu_eval_objective($evaluator(prob), x)                                          # moi.jl:1-3
@@ -190,7 +205,10 @@ function install!(nlp; into::Module=Main, kwargs...)
             $gpu_eval_constraint($evaluator(prob), g, x)                                      # moi.jl:10-13
         $MOI.eval_constraint_jacobian(prob::HybridNLP, vec, x) =
             $gpu_eval_constraint_jacobian($evaluator(prob), vec, x)                           # moi.jl:15-24 (uses `prob`, not the global `nlp`)
-        $MOI.features_available(prob::HybridNLP) = [:Grad, :Jac]                               # moi.jl:26-28
+        $MOI.features_available(prob::HybridNLP) = $feats                                     # moi.jl:26-28 (+ :Hess on request)
+        $MOI.hessian_lagrangian_structure(prob::HybridNLP) = $gpu_hessian_lagrangian_structure($evaluator(prob))
+        $MOI.eval_hessian_lagrangian(prob::HybridNLP, H, x, sigma, mu) =
+            $gpu_eval_hessian_lagrangian($evaluator(prob), H, x, sigma, mu)
         $MOI.initialize(prob::HybridNLP, features) = nothing                                   # moi.jl:30
         $MOI.jacobian_structure(prob::HybridNLP) = $gpu_jacobian_structure($evaluator(prob))   # moi.jl:31-33
     end)

@@ -208,6 +208,28 @@ QL_HD int ql_vals_run_off(const QlClass& c, int k)
 }
 QL_HD int ql_vals_nnz(const QlClass& c) { return ql_vals_run_off(c, c.N) + QL_VALS_LEN_LAST; }
 
+// ---- Lagrangian Hessian (no reference counterpart): block diagonal, one 20x20 block per knot
+// (15x15 for the last); values = lower triangle, column-major, restricted to the structural pattern of the knot's
+// mode (rk4_dual_gen.h: QL_HESS_R/C_MODE*; checked by static_assert in qlnlp_hess.cuh).
+#define QL_HESS_LEN_INIT 57      // modes 1 / 2 (the jump knot keeps the pattern; masked rows contribute zeros)
+#define QL_HESS_LEN_M3 55
+#define QL_HESS_LEN_LAST 15      // knot N: the diagonal (terminal cost + body-clearance d2/dtheta2)
+#define QL_HESS_PBUF 1832        // doubles of the per-pass staging buffer: 32 x 57 + parity, rounded to 16 B
+QL_HD int ql_hess_len(const QlClass& c, int k)
+{
+    if (k == c.N) return QL_HESS_LEN_LAST;
+    return k >= c.k_trans ? QL_HESS_LEN_M3 : QL_HESS_LEN_INIT;
+}
+QL_HD int ql_hess_run_off(const QlClass& c, int k)
+{
+    const int km = k - 1;                                         // knots before k
+    int n_init = c.k_trans - 1; if (n_init > km) n_init = km;     // ... of them in the initial mode
+    int hi = km < c.N - 1 ? km : c.N - 1;
+    int n_m3 = hi - (c.k_trans - 1); if (n_m3 < 0) n_m3 = 0;
+    return n_init * QL_HESS_LEN_INIT + n_m3 * QL_HESS_LEN_M3;
+}
+QL_HD int ql_hess_nnz(const QlClass& c) { return ql_hess_run_off(c, c.N) + QL_HESS_LEN_LAST; }
+
 QL_HD void ql_class_finish(QlClass* c) { c->nnz_true = ql_true_nnz(*c); c->nnz_vals = ql_vals_nnz(*c); }
 
 // ---- segments: what one bulk store moves ---------------------------------------------------

@@ -20,7 +20,7 @@
 
 #include "hostrows.h"
 #include "layout.h"
-#include "qlnlp_kernels.cuh"
+#include "qlnlp_hess.cuh"
 
 namespace {
 
@@ -140,6 +140,10 @@ struct qlnlp_handle_s {
     unsigned* ticket_pool = nullptr;             // pre-zeroed counters (128 B apart) so that a launch needs no
     int ticket_pool_used = 0;                    // allocation: launches stay legal inside CUDA-graph capture
     std::string pci_bus_id;
+    // Lagrangian Hessian (single evaluations on host pointers): device scratch x | lambda | values
+    double* d_hess_in = nullptr;
+    double* d_hess_out = nullptr;
+    int hess_blocks_per_sm = 0;
     size_t smem_per_sm = 0, smem_optin = 0;
     uint64_t serial = 0;               // unique per handle ever created (addresses get reused)
     std::map<std::vector<uint64_t>, RagTable> rag_tables;       // ragged launches led by this handle (key: the classes' serials)
@@ -668,6 +672,59 @@ int ragged_table(const qlnlp_handle* hs, int ncls, const RagTable** out)
     return QLNLP_OK;
 }
 
+// ---- Lagrangian Hessian ----------------------------------------------------------------------------------------
+void hessian_structure(const QlClass& c, int64_t* rows, int64_t* cols)
+{
+    int64_t n = 0;
+    for (int k = 1; k <= c.N; ++k) {
+        const int64_t base = (int64_t)QL_NZK * (k - 1);
+        if (k == c.N) {
+            for (int i = 0; i < QL_NX; ++i) { rows[n] = base + i + 1; cols[n] = base + i + 1; ++n; }
+            continue;
+        }
+        const int mode = (k >= c.k_trans) ? 3 : c.init_mode;
+        const int len = mode == 3 ? QL_HESS_LEN_MODE3 : QL_HESS_LEN_MODE1;
+        const unsigned char* R = mode == 1 ? QL_HESS_R_MODE1 : mode == 2 ? QL_HESS_R_MODE2 : QL_HESS_R_MODE3;
+        const unsigned char* C = mode == 1 ? QL_HESS_C_MODE1 : mode == 2 ? QL_HESS_C_MODE2 : QL_HESS_C_MODE3;
+        for (int e = 0; e < len; ++e) { rows[n] = base + R[e] + 1; cols[n] = base + C[e] + 1; ++n; }
+    }
+}
+
+int launch_hessian(qlnlp_handle h, int64_t B, const double* Z, int64_t ldz, const double* sigma, double sigma0,
+                   const double* lam, int64_t ldlam, double* H, int64_t ldh, cudaStream_t stream)
+{
+    const QlClass& c = h->cls;
+    if (B < 0) return fail(QLNLP_EINVAL, "negative batch");
+    if (B == 0) return QLNLP_OK;
+    if (!Z || !lam || !H) return fail(QLNLP_EINVAL, "Z, lambda and H are required");
+    if (ldz < c.n_nlp || ldlam < c.m_nlp || ldh < ql_hess_nnz(c)) return fail(QLNLP_EINVAL, "leading dimension too small");
+    const void* fn = h->fastdiv ? (const void*)ql::hess_kernel<true> : (const void*)ql::hess_kernel<false>;
+    const size_t smem = ql::hess_smem_bytes(c.N);
+    if (!h->hess_blocks_per_sm) {
+        if (smem > h->smem_optin) return fail(QLNLP_EINVAL, "N=%d needs %zu B of shared memory per warp", c.N, smem);
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, smem));
+        if (nb < 1) return fail(QLNLP_ECUDA, "Hessian kernel does not fit on an SM");
+        h->hess_blocks_per_sm = nb;
+    }
+    ql::HessLaunch P;
+    P.c = c;
+    P.rmb = h->rmb; P.rmf = h->rmf; P.rIb = h->rIb;
+    P.cost = h->d_cost; P.npad = h->npad;
+    P.Z = Z; P.ldz = ldz;
+    P.lam = lam; P.ldlam = ldlam;
+    P.sigma = sigma; P.sigma0 = sigma0;
+    P.H = H; P.ldh = ldh;
+    P.B = B;
+    P.bulk = ((reinterpret_cast<uintptr_t>(H) & 15) == 0 && (ldh & 1) == 0) ? 1 : 0;
+    P.zbulk = ((reinterpret_cast<uintptr_t>(Z) & 15) == 0 && (ldz & 1) == 0) ? 1 : 0;
+    const int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count * h->hess_blocks_per_sm);
+    void* args[] = {&P};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(QL_LANES), args, smem, stream));
+    return QLNLP_OK;
+}
+
 void free_lane(HostLane& ln)
 {
     if (ln.stage) cudaFreeHost(ln.stage);
@@ -1008,6 +1065,7 @@ void destroy_device_state(qlnlp_handle h)
     if (h->one.stream) cudaStreamDestroy(h->one.stream);
     if (h->one.hx) cudaFreeHost(h->one.hx);
     cudaFree(h->one.dx); cudaFree(h->one.dout);
+    cudaFree(h->d_hess_in); cudaFree(h->d_hess_out);
     for (auto& kv : h->rag_tables) cudaFree(kv.second.d_classes);
     cudaFree(h->ticket_pool);
     cudaFree(h->d_cost); cudaFree(h->d_x0xf); cudaFree(h->d_segs); cudaFree(h->d_seg_begin);
@@ -1394,6 +1452,62 @@ int qlnlp_host_free(void* ptr, int64_t bytes)
     if (cudaHostUnregister(ptr) != cudaSuccess) cudaGetLastError();
     munmap(ptr, len);
     return QLNLP_OK;
+}
+
+/* ---- Lagrangian Hessian.  No reference counterpart: src/moi.jl:26-28 offers [:Grad, :Jac]. ---- */
+int qlnlp_hessian_nnz(qlnlp_handle h, int64_t* nnz)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!nnz) return fail(QLNLP_EINVAL, "null output");
+    *nnz = ql_hess_nnz(h->cls);
+    return QLNLP_OK;
+}
+
+int qlnlp_hessian_structure(qlnlp_handle h, int64_t* rows, int64_t* cols)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!rows || !cols) return fail(QLNLP_EINVAL, "null output");
+    hessian_structure(h->cls, rows, cols);
+    return QLNLP_OK;
+}
+
+int qlnlp_eval_hessian_batch_device(qlnlp_handle h, int64_t B, const double* Z, int64_t ldz, const double* sigma,
+                                    const double* lambda, int64_t ldlambda, double* H, int64_t ldh, void* stream)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!h->subs.empty()) return fail(QLNLP_EINVAL, "multi-device handle: the Hessian takes a single-device handle");
+    if (B == 0) return QLNLP_OK;
+    DeviceGuard guard(h->device);
+    if (int rc = ensure_device(h)) return rc;
+    return launch_hessian(h, B, Z, ldz, sigma, 1.0, lambda, ldlambda, H, ldh, static_cast<cudaStream_t>(stream));
+}
+
+int qlnlp_eval_hessian_lagrangian(qlnlp_handle hh, const double* x, double sigma, const double* lambda, double* vals)
+{
+    if (int rc = check_handle(hh)) return rc;
+    if (!x || !lambda || !vals) return fail(QLNLP_EINVAL, "null argument");
+    qlnlp_handle h = first(hh);
+    const QlClass& c = h->cls;
+    DeviceGuard guard(h->device);
+    if (int rc = ensure_device(h)) return rc;
+    const int64_t ldl = (c.m_nlp + 1) & ~1, ldh = (ql_hess_nnz(c) + 1) & ~1;
+    if (!h->d_hess_in) {
+        CUDA_TRY(cudaMalloc(&h->d_hess_in, sizeof(double) * (h->ldz_e + ldl)));
+        CUDA_TRY(cudaMalloc(&h->d_hess_out, sizeof(double) * ldh));
+    }
+    cudaStream_t s = h->one.stream;
+    CUDA_TRY(cudaMemcpyAsync(h->d_hess_in, x, sizeof(double) * c.n_nlp, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_hess_in + h->ldz_e, lambda, sizeof(double) * c.m_nlp, cudaMemcpyHostToDevice, s));
+    int rc = launch_hessian(h, 1, h->d_hess_in, h->ldz_e, nullptr, sigma, h->d_hess_in + h->ldz_e, ldl, h->d_hess_out, ldh, s);
+    if (rc == QLNLP_OK) {
+        cudaError_t e = cudaMemcpyAsync(vals, h->d_hess_out, sizeof(double) * ql_hess_nnz(c), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = fail(QLNLP_ECUDA, "Hessian: %s", cudaGetErrorString(e));
+    }
+    const std::string msg = g_err;
+    const cudaError_t es = cudaStreamSynchronize(s);      // also on the error path: x / lambda / vals are caller-owned
+    if (rc == QLNLP_OK && es != cudaSuccess) return fail(QLNLP_ECUDA, "Hessian: %s", cudaGetErrorString(es));
+    g_err = msg;
+    return rc;
 }
 
 int qlnlp_eval_all(qlnlp_handle h, const double* x, double* f, double* grad, double* g, double* vals)

@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "qlnlp_eval_batch_device_multi", "qlnlp_synchronize", "qlnlp_host_output_register", "qlnlp_host_output_unregister",
     "qlnlp_host_pin", "qlnlp_host_unpin", "qlnlp_host_path_info", "qlnlp_host_alloc", "qlnlp_host_free",
     "qlnlp_eval_ragged_classes",
+    "qlnlp_hessian_nnz", "qlnlp_hessian_structure", "qlnlp_eval_hessian_lagrangian", "qlnlp_eval_hessian_batch_device",
 )
 _DEBUG_SYMBOLS = ("qlnlp_debug_segments", "qlnlp_debug_vals_map", "qlnlp_debug_build_rows", "qlnlp_debug_host_times")
 
@@ -120,6 +121,10 @@ def load_library(rebuild_if_stale: bool = True):
     L.qlnlp_host_pin.argtypes = [vp, C.c_int64]
     L.qlnlp_host_unpin.argtypes = [vp]
     L.qlnlp_host_path_info.argtypes = [vp, i64p]
+    L.qlnlp_hessian_nnz.argtypes = [vp, i64p]
+    L.qlnlp_hessian_structure.argtypes = [vp, vp, vp]
+    L.qlnlp_eval_hessian_lagrangian.argtypes = [vp, vp, C.c_double, vp, vp]
+    L.qlnlp_eval_hessian_batch_device.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, vp]
     L.qlnlp_host_alloc.argtypes = [C.c_int64, C.POINTER(vp)]
     L.qlnlp_host_free.argtypes = [vp, C.c_int64]
     for name in [n for n in EXPORTED_SYMBOLS if n not in ("qlnlp_version", "qlnlp_last_error")] + list(_DEBUG_SYMBOLS):
@@ -193,19 +198,23 @@ class HybridNLP:
 
     def __init__(self, model: PlanarQuadruped, obj: Sequence[QuadraticCost], init_mode: int, k_trans: int,
                  N: int, x0, xf, integration: str = "RK4", *, use_sparse_jacobian: bool = False,
-                 pattern: str = "block", device: int = 0, devices: Optional[Sequence[int]] = None):
+                 pattern: str = "block", device: int = 0, devices: Optional[Sequence[int]] = None,
+                 hessian: bool = False):
         if integration != "RK4":
             raise ValueError("only RK4 is implemented (as in the reference)")
         self._init(ProblemData.from_costs(model, obj, init_mode, k_trans, N, x0, xf), use_sparse_jacobian, device, pattern,
                    devices)
+        self.hessian = bool(hessian)
 
     @classmethod
     def from_problem(cls, prob: ProblemData, *, use_sparse_jacobian: bool = True, pattern: str = "block",
-                     device: int = 0, devices: Optional[Sequence[int]] = None) -> "HybridNLP":
+                     device: int = 0, devices: Optional[Sequence[int]] = None, hessian: bool = False) -> "HybridNLP":
         """``devices=[0, 1, ...]`` builds a multi-device evaluator (``qlnlp_create_multi``): host-pointer batches are
-        sharded over the listed GPUs by the library, ``eval_batch_multi`` launches one shard per device."""
+        sharded over the listed GPUs by the library, ``eval_batch_multi`` launches one shard per device.
+        ``hessian=True`` advertises ``"Hess"`` (the reference does not, src/moi.jl:26-28)."""
         self = cls.__new__(cls)
         self._init(prob, use_sparse_jacobian, device, pattern, devices)
+        self.hessian = bool(hessian)
         return self
 
     def _init(self, prob: ProblemData, use_sparse_jacobian: bool, device: int, pattern: str = "block",
@@ -239,6 +248,10 @@ class HybridNLP:
             arr = (C.c_int * len(self.devices))(*self.devices)
             _check(L.qlnlp_create_multi(C.byref(d), arr, len(self.devices), mode, C.byref(self._h)))
         self._registered = {}
+        self.hessian = False
+        nh = C.c_int64()
+        _check(L.qlnlp_hessian_nnz(self._h, C.byref(nh)))
+        self.nnz_hess = nh.value
         n, mm, nnz, nnzb = (C.c_int64() for _ in range(4))
         _check(L.qlnlp_dims(self._h, C.byref(n), C.byref(mm), C.byref(nnz), C.byref(nnzb)))
         self.n_nlp, self.m_nlp, self.nnz, self.nnz_block = n.value, mm.value, nnz.value, nnzb.value
@@ -278,7 +291,43 @@ class HybridNLP:
 
     # ---- MOI surface, moi.jl:1-33
     def features_available(self) -> List[str]:
-        return ["Grad", "Jac"]                            # moi.jl:26-28
+        return ["Grad", "Jac", "Hess"] if self.hessian else ["Grad", "Jac"]      # moi.jl:26-28 (+ opt-in :Hess)
+
+    # ---- Lagrangian Hessian (MOI.hessian_lagrangian_structure / eval_hessian_lagrangian; not in the reference)
+    def hessian_lagrangian_structure(self) -> List[Tuple[int, int]]:
+        rows, cols = self.hessian_structure_arrays()
+        return list(zip(rows.tolist(), cols.tolist()))
+
+    def hessian_structure_arrays(self) -> Tuple[np.ndarray, np.ndarray]:
+        rows = np.empty(self.nnz_hess, dtype=np.int64)
+        cols = np.empty(self.nnz_hess, dtype=np.int64)
+        _check(load_library().qlnlp_hessian_structure(self._h, _np_ptr(rows), _np_ptr(cols)))
+        return rows, cols
+
+    def eval_hessian_lagrangian(self, H: np.ndarray, x, sigma: float, mu) -> None:
+        """``H[nnz_hess]`` <- sigma * Hess f(x) + sum_r mu_r Hess g_r(x) in ``hessian_lagrangian_structure`` order."""
+        self._out(H, self.nnz_hess, "H")
+        mu = self._x(mu, self.m_nlp)
+        _check(load_library().qlnlp_eval_hessian_lagrangian(self._h, _np_ptr(self._x(x, self.n_nlp)), float(sigma),
+                                                            _np_ptr(mu), _np_ptr(H)))
+
+    def eval_hessian_batch(self, Z, mu, sigma=None, out=None, stream=None):
+        """Device tensors: ``Z[B, n_nlp]``, ``mu[B, m_nlp]``, optional ``sigma[B]`` (default 1) -> ``H[B, nnz_hess]``."""
+        import torch
+
+        B = Z.shape[0]
+        for t, w, name in ((Z, self.n_nlp, "Z"), (mu, self.m_nlp, "mu")):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.shape == (B, w) and t.stride(1) == 1):
+                raise ValueError(f"{name} must be a float64 CUDA tensor [B, {w}]")
+        if out is None:
+            out = torch.empty((B, even_ld(self.nnz_hess)), dtype=torch.float64, device=Z.device)[:, :self.nnz_hess]
+        s = torch.cuda.current_stream(Z.device) if stream is None else stream
+        ld = lambda t, w: t.stride(0) if B > 1 else even_ld(w)
+        _check(load_library().qlnlp_eval_hessian_batch_device(
+            self._h, B, C.c_void_p(Z.data_ptr()), Z.stride(0) if B > 1 else self.n_nlp,
+            None if sigma is None else C.c_void_p(sigma.data_ptr()), C.c_void_p(mu.data_ptr()),
+            mu.stride(0) if B > 1 else self.m_nlp, C.c_void_p(out.data_ptr()), ld(out, self.nnz_hess), C.c_void_p(s.cuda_stream)))
+        return out
 
     def initialize(self, features: Iterable[str] = ()) -> None:
         return None                                       # moi.jl:30

@@ -63,6 +63,7 @@ def emul_lib():
     L.emul_jac_stream.argtypes = [C.c_int] * 3 + [C.c_double] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.emul_true_stream.argtypes = [C.c_int] * 3 + [C.c_double] * 4 + [C.c_void_p, C.c_void_p, C.c_int]
     L.emul_vals_stream.argtypes = [C.c_int] * 3 + [C.c_double] * 4 + [C.c_void_p, C.c_void_p, C.c_int]
+    L.emul_hess_stream.argtypes = [C.c_int] * 3 + [C.c_double] * 4 + [C.c_void_p] * 5 + [C.c_double, C.c_void_p, C.c_void_p, C.c_int]
     L.emul_run_off.argtypes = [C.c_int] * 4
     L.emul_rk4_pos.argtypes = [C.c_int] * 6
     return L

@@ -136,6 +136,46 @@ int emul_vals_stream(int N, int k_trans, int init_mode, double g, double mb, dou
     return 0;
 }
 
+// Lagrangian-Hessian stream exactly as the kernel assembles it (qlnlp_hess.cuh): every knot writes its block at
+// ql_hess_run_off with the generated second-order code.  cost: knot-major Q[N][15] R[N][5] q[N][15] r[N][5].
+int emul_hess_stream(int N, int k_trans, int init_mode, double g, double mb, double mf, double lb,
+                     const double* Q, const double* R, const double* q, const double* r,
+                     const double* Z, double sigma, const double* lambda, double* out, int nout)
+{
+    QlClass c;
+    ql_class_init(&c, N, k_trans, init_mode, g, mb, mf, lb);
+    ql_class_finish(&c);
+    if (nout != ql_hess_nnz(c)) return -1;
+    const HostConsts K{c.g, c.mb, c.mf, c.Ib};
+    for (int i = 0; i < nout; ++i) out[i] = NAN;
+    for (int k = 1; k <= N; ++k) {
+        const double* x = Z + 20 * (k - 1);
+        const double* u = x + 15;
+        const int off = ql_hess_run_off(c, k);
+        if (off < 0 || off + ql_hess_len(c, k) > nout) return -2;
+        if (k < N && off + ql_hess_len(c, k) != ql_hess_run_off(c, k + 1)) return -3;
+        const double as = c.half_lb * std::sin(x[2]);
+        const double tt = lambda[c.c_body + (k - 1)] * ((x[2] > 0) ? as : -as);
+        const double* Qk = Q + 15 * (k - 1);
+        if (k == N) {
+            for (int i = 0; i < 15; ++i) out[off + i] = (i == 2) ? sigma * Qk[i] + tt : sigma * Qk[i];
+            continue;
+        }
+        double lam[15], hv[QL_NH_MODE1], ox[15], ou[4], hx[15], hu[4];
+        for (int i = 0; i < 15; ++i) lam[i] = lambda[c.c_dyn + 15 * (k - 1) + i];
+        if (k == k_trans - 1) { lam[4] = lam[6] = lam[10] = lam[11] = lam[12] = lam[13] = 0.0; }
+        const double h = u[4];
+        const double *Rk = R + 5 * (k - 1), *qk = q + 15 * (k - 1), *rk = r + 5 * (k - 1);
+        for (int i = 0; i < 15; ++i) { ox[i] = sigma * (h * Qk[i]); hx[i] = sigma * (Qk[i] * x[i] + qk[i]); }
+        for (int i = 0; i < 4; ++i) { ou[i] = sigma * (h * Rk[i]); hu[i] = sigma * (Rk[i] * u[i] + rk[i]); }
+        const double hh = sigma * (2.0 * (Rk[4] * h + rk[4]) + h * Rk[4]);
+        if (k >= k_trans) { ql_rk4_hess_mode3(x, u, K, lam, hv); ql_hess_store_mode3(hv, ox, ou, hx, hu, hh, tt, out + off); }
+        else if (init_mode == 1) { ql_rk4_hess_mode1(x, u, K, lam, hv); ql_hess_store_mode1(hv, ox, ou, hx, hu, hh, tt, out + off); }
+        else { ql_rk4_hess_mode2(x, u, K, lam, hv); ql_hess_store_mode2(hv, ox, ou, hx, hu, hh, tt, out + off); }
+    }
+    return 0;
+}
+
 // closed-form helpers exposed for direct checks
 int emul_run_off(int N, int k_trans, int init_mode, int k)
 {

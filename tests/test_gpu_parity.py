@@ -606,3 +606,40 @@ def test_multi_device_handle_shards_the_batch(golden):
     assert torch.cuda.current_device() == 0
     with pytest.raises(ql.QlnlpError):
         multi.eval_batch(Zs[0])
+
+
+@pytest.mark.parametrize("N,kt,im,B", [(61, 21, 1, 300), (61, 21, 2, 64), (31, 11, 2, 64), (2, 1, 1, 40), (2, 2, 2, 40),
+                                       (33, 33, 1, 64), (33, 1, 2, 64), (65, 2, 1, 64), (121, 41, 1, 33)])
+def test_lagrangian_hessian_against_the_oracle(N, kt, im, B):
+    """SURVEY.md 8f N3 (no reference target: src/moi.jl:26-28): sigma Hess f + sum_r mu_r Hess g_r from the kernel
+    generated out of second-order duals vs the oracle's dense second-order forward mode, batched and single."""
+    p = ql.build_problem(N=N, k_trans=kt, init_mode=im)
+    nlp, o = ql.HybridNLP.from_problem(p, hessian=True), Oracle(p)
+    rng = np.random.default_rng(N + kt)
+    base = ql.initial_guess(p) if kt > 1 else np.zeros(p.n_nlp)
+    Z = perturbed_batch(p, [base], B, 5e-2, 9)
+    mu = rng.standard_normal((B, p.m_nlp))
+    sigma = rng.uniform(0.2, 2.0, size=B)
+    rows, cols = nlp.hessian_structure_arrays()
+    for padded in (False, True):
+        if padded:
+            Zd = torch.zeros((B, p.n_nlp + 1), dtype=torch.float64, device="cuda")[:, :p.n_nlp]
+            Zd.copy_(torch.from_numpy(Z))
+        else:
+            Zd = torch.from_numpy(Z).cuda()
+        H = nlp.eval_hessian_batch(Zd, torch.from_numpy(mu).cuda(), torch.from_numpy(sigma).cuda())
+        torch.cuda.synchronize()
+        H = H.cpu().numpy()
+        for b in range(0, B, max(1, B // 6)):
+            want = o.hess_lagrangian_dense(Z[b], sigma[b], mu[b])[rows - 1, cols - 1]
+            tol = 1e-12 * max(1.0, np.abs(want).max())
+            assert np.abs(H[b] - want).max() <= tol, (b, padded)
+    # the MOI-style single call on host pointers
+    vals = np.empty(nlp.nnz_hess)
+    nlp.eval_hessian_lagrangian(vals, Z[1], sigma[1], mu[1])
+    assert np.array_equal(vals, H[1])
+    # position independence
+    H2 = nlp.eval_hessian_batch(torch.from_numpy(Z[::-1].copy()).cuda(), torch.from_numpy(mu[::-1].copy()).cuda(),
+                                torch.from_numpy(sigma[::-1].copy()).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(H2.cpu().numpy()[::-1], H)

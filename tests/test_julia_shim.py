@@ -18,6 +18,7 @@ ACCEPT = {
     "const qlnlp_batch_io*": {"Ref{QlBatchIO}", "Ptr{QlBatchIO}"},
     "int": {"Cint"},
     "int64_t": {"Int64"},
+    "double": {"Cdouble"},
     "const int*": {"Ptr{Cint}", "Ref{Cint}"},
     "int*": {"Ptr{Cint}", "Ref{Cint}"},
     "const double*": {"Ptr{Cdouble}", "Ref{Cdouble}"},

@@ -167,9 +167,68 @@ class Dual:
         return Dual(g, g.mul(c, self.v), {j: g.mul(n, c) for j, n in self.p.items()})
 
 
+class Dual2:
+    """Second-order forward-mode number: value, gradient {j: node}, Hessian {(j, l), j <= l: node}.  Used for the
+    Lagrangian Hessian (no reference counterpart: src/moi.jl:26-28 offers [:Grad, :Jac] only)."""
+    __slots__ = ("g", "v", "p", "h")
+
+    def __init__(self, g, v, p=None, h=None):
+        self.g = g
+        self.v = v
+        self.p = {j: n for j, n in (p or {}).items() if n != g.zero}
+        self.h = {k: n for k, n in (h or {}).items() if n != g.zero}
+
+    def part(self, j):
+        return self.p.get(j, self.g.zero)
+
+    def hess(self, j, l):
+        return self.h.get((j, l) if j <= l else (l, j), self.g.zero)
+
+    def _lin(self, o, op):
+        g = self.g
+        return Dual2(g, op(self.v, o.v), {j: op(self.part(j), o.part(j)) for j in sorted(set(self.p) | set(o.p))},
+                     {k: op(self.h.get(k, g.zero), o.h.get(k, g.zero)) for k in sorted(set(self.h) | set(o.h))})
+
+    def add(self, o):
+        return self._lin(o, self.g.add)
+
+    def sub(self, o):
+        return self._lin(o, self.g.sub)
+
+    def neg(self):
+        g = self.g
+        return Dual2(g, g.neg(self.v), {j: g.neg(n) for j, n in self.p.items()}, {k: g.neg(n) for k, n in self.h.items()})
+
+    def mul(self, y):
+        # (xy)' = y x' + x y';  (xy)'' = (y x'' + x y'') + (x'_j y'_l + x'_l y'_j)
+        g, x = self.g, self
+        p = {j: g.add(g.mul(y.v, x.part(j)), g.mul(x.v, y.part(j))) for j in sorted(set(x.p) | set(y.p))}
+        keys = set(x.h) | set(y.h)
+        for j in x.p:
+            for l in y.p:
+                keys.add((min(j, l), max(j, l)))
+        h = {}
+        for (j, l) in sorted(keys):
+            t = g.add(g.mul(y.v, x.hess(j, l)), g.mul(x.v, y.hess(j, l)))
+            c = g.add(g.mul(x.part(j), y.part(l)), g.mul(x.part(l), y.part(j)))
+            h[(j, l)] = g.add(t, c)
+        return Dual2(g, g.mul(x.v, y.v), p, h)
+
+    def divc(self, c):
+        g = self.g
+        return Dual2(g, g.div(self.v, c), {j: g.div(n, c) for j, n in self.p.items()}, {k: g.div(n, c) for k, n in self.h.items()})
+
+    def addc(self, c):
+        return Dual2(self.g, self.g.add(self.v, c), dict(self.p), dict(self.h))
+
+    def mulc(self, c):
+        g = self.g
+        return Dual2(g, g.mul(c, self.v), {j: g.mul(n, c) for j, n in self.p.items()}, {k: g.mul(n, c) for k, n in self.h.items()})
+
+
 def contact_dynamics(g, mode, x, u, P):
     """planar_quadruped.jl:36-79 / :89-132 / :142-185 on Duals (x: 14, u: 5)."""
-    zero = Dual(g, g.zero)
+    zero = type(x[0])(g, g.zero)
     xb, yb = x[0], x[1]
     x1, y1 = x[3], x[4]
     x2, y2 = x[5], x[6]
@@ -219,6 +278,27 @@ def rk4(g, mode, x, u, P):
         xn.append(x[i].add(h6.mul(s)))
     xn.append(x[14].add(u[4]))
     return xn
+
+
+def build_hessian(mode):
+    """lambda-contracted Hessian of one RK4 step: {(row, col), row >= col: node} with lam[i] as inputs."""
+    g = Graph()
+    P = {n: g.inp(n) for n in ("g", "mb", "mf", "Ib")}
+    z = [Dual2(g, g.inp(f"x[{j}]" if j < NX else f"u[{j - NX}]"), {j: g.one}) for j in range(NP)]
+    xn = rk4(g, mode, z[:NX], z[NX:], P)
+    lam = [g.inp(f"lam[{i}]") for i in range(NX)]
+    keys = set()
+    for i in range(NX):
+        keys |= set(xn[i].h)
+    ent = {}
+    for (j, l) in keys:                       # j <= l  ->  lower-triangle entry (row l, column j)
+        acc = g.zero
+        for i in range(NX):
+            n = xn[i].h.get((j, l))
+            if n is not None:
+                acc = g.add(acc, g.mul(lam[i], n))
+        ent[(l, j)] = acc
+    return g, ent
 
 
 def build(mode, with_partials):
@@ -461,6 +541,52 @@ def main():
             w("}")
             w("")
         summary.append((mode, "jac", cnt, len(var), len(con)))
+        # ---- Lagrangian Hessian block of a knot (N3): sum_i lam_i Hess(rk4_i) + sigma Hess(h * stagecost) + the
+        # body-clearance row's d2/dtheta2, lower triangle of the 20x20 block in column-major order -----------------
+        gh, ent = build_hessian(mode)
+        hkeys = sorted(ent, key=lambda rc: (rc[1], rc[0]))             # by (column, row)
+        lines, cnt = emit_body(gh, [(f"hv[{n}]", ent[k]) for n, k in enumerate(hkeys)])
+        w(f"// mode {mode}, lambda-contracted Hessian of the RK4 step: {len(hkeys)} entries of the lower triangle: {cnt}")
+        w(f"#define QL_NH_MODE{mode} {len(hkeys)}")
+        w(f"template <typename KT>")
+        w(f"QL_FN void ql_rk4_hess_mode{mode}(const double* x, const double* u, const KT& K, const double* lam, double* hv)")
+        w("{")
+        out.extend(lines)
+        w("}")
+        w("")
+        # objective: f_k = h * stagecost(x, u) (costs.jl:12): d2/dx_i2 = h Q_ii, d2/du_i2 = h R_ii (i < 4),
+        # d2/dh dx_i = (Qx+q)_i, d2/dh du_i = (Ru+r)_i, d2/dh2 = 2 (R_55 h + r_5) + h R_55; all times sigma
+        obj = {(i, i): f"ox[{i}]" for i in range(NX)}
+        obj.update({(NX + i, NX + i): f"ou[{i}]" for i in range(NU - 1)})
+        obj.update({(NP - 1, i): f"hx[{i}]" for i in range(NX)})
+        obj.update({(NP - 1, NX + i): f"hu[{i}]" for i in range(NU - 1)})
+        obj[(NP - 1, NP - 1)] = "hh"
+        union = sorted(set(hkeys) | set(obj) | {(2, 2)}, key=lambda rc: (rc[1], rc[0]))
+        hidx = {k: n for n, k in enumerate(hkeys)}
+        w(f"// union pattern of a knot's Hessian block in mode {mode}: {len(union)} entries (row, col), row >= col, column-major")
+        w(f"#define QL_HESS_LEN_MODE{mode} {len(union)}")
+        w(f"static const unsigned char QL_HESS_R_MODE{mode}[{len(union)}] = {{{', '.join(str(r) for r, _ in union)}}};")
+        w(f"static const unsigned char QL_HESS_C_MODE{mode}[{len(union)}] = {{{', '.join(str(c) for _, c in union)}}};")
+        w(f"// writes the block: RK4 part (hv) + objective part (ox, ou, hx, hu, hh: already scaled by sigma) + tt on (theta, theta)")
+        w(f"template <typename PTR>")
+        w(f"QL_FN void ql_hess_store_mode{mode}(const double* hv, const double* ox, const double* ou, const double* hx,")
+        w(f"                                   const double* hu, double hh, double tt, PTR run)")
+        w("{")
+        for pos, k in enumerate(union):
+            terms = []
+            if k in hidx:
+                terms.append(f"hv[{hidx[k]}]")
+            if k in obj:
+                terms.append(obj[k])
+            if k == (2, 2):
+                terms.append("tt")
+            expr = terms[0]
+            for t in terms[1:]:
+                expr = f"QL_ADD({expr}, {t})"
+            w(f"    QL_ST(run, {pos}, {expr});")
+        w("}")
+        w("")
+        summary.append((mode, "hess", cnt, len(hkeys), len(union)))
     text = "\n".join(out) + "\n"
     with open(OUT, "w") as f:
         f.write(text)
