@@ -643,3 +643,12 @@ def test_lagrangian_hessian_against_the_oracle(N, kt, im, B):
                                 torch.from_numpy(sigma[::-1].copy()).cuda())
     torch.cuda.synchronize()
     assert np.array_equal(H2.cpu().numpy()[::-1], H)
+
+
+def test_empty_batches_are_not_an_error(dflt):
+    """An empty shard (B = 0) returns empty outputs without touching the device (sharding with B < world size)."""
+    p, nlp, o = dflt
+    out = nlp.eval_batch(torch.empty((0, p.n_nlp), dtype=torch.float64, device="cuda"))
+    assert out["jac"].shape == (0, nlp.nnz_block) and out["f"].shape == (0,)
+    host = nlp.eval_batch_host(np.empty((0, p.n_nlp)))
+    assert host["g"].shape == (0, nlp.m_nlp)
