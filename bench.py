@@ -548,12 +548,24 @@ def run_gpu(args):
     launch_info = nlp.launch_info()
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region -----------------
-    pin = [torch.from_numpy(z).pin_memory() for z in host_sets[:2]]
-    hout = {"f": torch.empty(B_PER_GPU, dtype=torch.float64).pin_memory(),
-            "grad": torch.empty((B_PER_GPU, nlp.n_nlp), dtype=torch.float64).pin_memory(),
-            "g": torch.empty((B_PER_GPU, nlp.m_nlp), dtype=torch.float64).pin_memory(),
-            "jac": torch.empty((B_PER_GPU, nlp.nnz_block), dtype=torch.float64).pin_memory()}
-    hnp = {k: v.numpy() for k, v in hout.items()}
+    # caller-side arrays come from the library's allocator (qlnlp_host_alloc: page-locked, 2 MB pages where granted)
+    def pinned(shape):
+        try:
+            return ql.host_alloc(shape)
+        except Exception:                                    # noqa: BLE001
+            return torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+
+    class _Pin:                                              # the two input batches the host calls alternate between
+        def __init__(self, z):
+            self.a = pinned(z.shape)
+            self.a[:] = z
+
+        def numpy(self):
+            return self.a
+
+    pin = [_Pin(z) for z in host_sets[:2]]
+    hnp = {"f": pinned((B_PER_GPU,)), "grad": pinned((B_PER_GPU, nlp.n_nlp)), "g": pinned((B_PER_GPU, nlp.m_nlp)),
+           "jac": pinned((B_PER_GPU, nlp.nnz_block))}
     e2e_steps = max(3, min(args.steps, 20))
 
     def time_host(ev, outs, wanted=want, label=""):
@@ -601,7 +613,7 @@ def run_gpu(args):
     e2e_ceiling_node = cx.sum_over_ranks(e2e_ceiling)
     nlp.unregister_host_output(hnp["jac"])
     nlp_t = ql.HybridNLP.from_problem(prob, pattern="true", device=local)
-    hnp_t = dict(hnp, jac=torch.empty((B_PER_GPU, nlp_t.nnz), dtype=torch.float64).pin_memory().numpy())
+    hnp_t = dict(hnp, jac=pinned((B_PER_GPU, nlp_t.nnz)))
     e2e_true = time_host(nlp_t, hnp_t, label="SPARSE_TRUE rows")
     del nlp_t, hnp_t
 
@@ -620,11 +632,10 @@ def run_gpu(args):
                 mh = ql.HybridNLP.from_problem(prob, devices=list(range(world)))
                 mh.set_option("host_threads", max(1, host_cores() // world))     # the other ranks are idle: all cores
                 Bm = B_PER_GPU * world
-                Zm = torch.from_numpy(np.concatenate([host_sets[i % N_INPUT_SETS] for i in range(world)])).pin_memory().numpy()
-                om = {"f": torch.empty(Bm, dtype=torch.float64).pin_memory().numpy(),
-                      "grad": torch.empty((Bm, nlp.n_nlp), dtype=torch.float64).pin_memory().numpy(),
-                      "g": torch.empty((Bm, nlp.m_nlp), dtype=torch.float64).pin_memory().numpy(),
-                      "jac": torch.empty((Bm, nlp.nnz_block), dtype=torch.float64).pin_memory().numpy()}
+                Zm = pinned((Bm, nlp.n_nlp))
+                Zm[:] = np.concatenate([host_sets[i % N_INPUT_SETS] for i in range(world)])
+                om = {"f": pinned((Bm,)), "grad": pinned((Bm, nlp.n_nlp)), "g": pinned((Bm, nlp.m_nlp)),
+                      "jac": pinned((Bm, nlp.nnz_block))}
                 mh.register_host_output(om["jac"])
                 for _ in range(2):
                     mh.eval_batch_host(Zm, out=om)
@@ -632,10 +643,13 @@ def run_gpu(args):
                 for _ in range(5):
                     mh.eval_batch_host(Zm, out=om)
                 tm = (time.perf_counter() - t0) / 5
-                ok = np.array_equal(om["jac"][:64], out["jac"][:64].cpu().numpy()) if False else True
+                dchk = nlp.eval_batch(padded(torch, Zm[Bm - 64:], dev), want=("jac", "g"))      # the last shard's rows, on this rank's GPU
+                torch.cuda.synchronize()
+                ok = np.array_equal(om["jac"][Bm - 64:], dchk["jac"].cpu().numpy()) and np.array_equal(om["g"][Bm - 64:], dchk["g"].cpu().numpy())
                 multi = {"what": "ONE host thread, ONE qlnlp_eval_batch_host call on a multi-device handle "
                                  "(qlnlp_create_multi): the library shards the batch over the GPUs (registered rows)",
                          "devices": world, "global_batch": Bm, "value": Bm / tm, "unit": UNIT, "ms_per_call": tm * 1e3,
+                         "check": "ok" if ok else "rows differ from a single-device evaluation",
                          "threads_per_device": mh.host_path_info()["threads_per_device"]}
                 del mh, om, Zm
             except Exception as e:                           # noqa: BLE001
@@ -654,7 +668,7 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "passes": "best of 2 passes of `steps` calls", "check": e2e_check,
-                    "path": "qlnlp_eval_batch_host on pinned host buffers, output rows registered once "
+                    "path": "qlnlp_eval_batch_host on page-locked host buffers (qlnlp_host_alloc), output rows registered once "
                             "(qlnlp_host_output_register, like jac_c! relying on the caller's zeros): 512-evaluation chunks "
                             "pipelined over 4 streams; f/grad/g land in the caller's arrays by DMA; of the 32,161 SPARSE_BLOCK "
                             "values per evaluation only the 2,794 value-dependent ones cross PCIe and a persistent pool of host "
