@@ -149,6 +149,12 @@ int qlnlp_eval_hessian_lagrangian(qlnlp_handle h, const double* x, double sigma,
 int qlnlp_eval_hessian_batch_device(qlnlp_handle h, int64_t B, const double* Z, int64_t ldz, const double* sigma,
                                     const double* lambda, int64_t ldlambda, double* H, int64_t ldh, void* stream);
 
+/* Initial guesses of a sweep on the device (notebook cell 7, src/main.ipynb:181-196):
+ * Z[b] = `base` (the class guess: packZ(nlp, Xguess, Uref) for the handle's own x0, n_nlp doubles) with the first 14
+ * states of knots 1..k_trans replaced by  x0[b] + (xterm - x0[b]) / (k_trans - 1) * (k - 1).  Device pointers. */
+int qlnlp_initial_guess_batch_device(qlnlp_handle h, int64_t B, const double* base, const double* x0, double* Z,
+                                     int64_t ldz, void* stream);
+
 /* ---- batched evaluation (B independent decision vectors; no reference equivalent) -------- */
 typedef struct {
     const double* Z;   int64_t ldz;     /* [B][ldz],    ldz    >= n_nlp          (required).  With Z 16-byte aligned

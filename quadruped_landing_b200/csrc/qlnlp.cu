@@ -781,7 +781,26 @@ int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
 {
     const QlClass& c = h->cls;
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, env_int("QLNLP_HOST_CHUNK", (int)h->opt_host_chunk)));
-    const int64_t nchunks = (B + chunk - 1) / chunk;
+    // Chunk schedule: uniform chunks.  QLNLP_HOST_RAMP=1 puts a quarter and a half chunk at either end (the first rows
+    // reach the row builder sooner, the last build is shorter); measured: no consistent gain (875 / 840 vs 856 / 855 k
+    // evals/s, profiles/r02_host_path.md) -- the D2H copies, not the fill, bound the pipeline -- so it is off.
+    std::vector<int64_t> c_start, c_size;
+    {
+        std::vector<int64_t> front, back;
+        if (B >= 3 * chunk && chunk >= 64 && env_flag("QLNLP_HOST_RAMP", false)) {
+            front = {chunk / 4, chunk / 2};
+            back = {chunk / 2, chunk / 4};
+        }
+        int64_t pos = 0, tail = 0;
+        for (int64_t v : back) tail += v;
+        for (int64_t v : front) { c_start.push_back(pos); c_size.push_back(v); pos += v; }
+        while (B - tail - pos > 0) {
+            const int64_t v = std::min(chunk, B - tail - pos);
+            c_start.push_back(pos); c_size.push_back(v); pos += v;
+        }
+        for (int64_t v : back) { c_start.push_back(pos); c_size.push_back(v); pos += v; }
+    }
+    const int64_t nchunks = (int64_t)c_start.size();
     const int nlanes = (int)std::min<int64_t>(MAX_LANES, nchunks);
     for (int l = 0; l < nlanes; ++l)
         if (int rc = reserve_lane(h, h->lanes[l], chunk)) return rc;
@@ -806,7 +825,7 @@ int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
     auto enqueue = [&](int64_t i) -> int {
         const double t0 = now();
         HostLane& ln = h->lanes[i % nlanes];
-        const int64_t b0 = i * chunk, nb = std::min(chunk, B - b0);
+        const int64_t b0 = c_start[(size_t)i], nb = c_size[(size_t)i];
         cudaStream_t s = ln.stream;
         CUDA_TRY(copy_rows(ln.Z, ldz_d, io->Z + b0 * io->ldz, io->ldz, c.n_nlp, nb, cudaMemcpyHostToDevice, s));
         if (io->x0) CUDA_TRY(cudaMemcpyAsync(ln.x0, io->x0 + b0 * QL_NX, sizeof(double) * nb * QL_NX, cudaMemcpyHostToDevice, s));
@@ -855,7 +874,7 @@ int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
             h->stat_t_wait += now() - t0;
             if (q == cudaErrorNotReady) return QLNLP_OK;
             if (q != cudaSuccess) return fail(QLNLP_ECUDA, "host pipeline: %s", cudaGetErrorString(q));
-            const int64_t b0 = handed * chunk, nb = std::min(chunk, B - b0);
+            const int64_t b0 = c_start[(size_t)handed], nb = c_size[(size_t)handed];
             double* rows = io->jac + b0 * io->ldjac;
             t_build0 = now();
             h->plan->build_async(h->pool.get(), ln.stage, h->ldv_e, rows, io->ldjac, nb, touched_only);
@@ -1508,6 +1527,26 @@ int qlnlp_eval_hessian_lagrangian(qlnlp_handle hh, const double* x, double sigma
     if (rc == QLNLP_OK && es != cudaSuccess) return fail(QLNLP_ECUDA, "Hessian: %s", cudaGetErrorString(es));
     g_err = msg;
     return rc;
+}
+
+/* Batched initial guesses on the device (main.ipynb:181-196): Z[b] = the class guess `base` with the
+ * first 14 states of knots 1..k_trans interpolated from x0[b] to the handle's terminal state.  All device pointers. */
+int qlnlp_initial_guess_batch_device(qlnlp_handle hh, int64_t B, const double* base, const double* x0, double* Z,
+                                     int64_t ldz, void* stream)
+{
+    if (int rc = check_handle(hh)) return rc;
+    if (B == 0) return QLNLP_OK;
+    if (B < 0 || !base || !x0 || !Z) return fail(QLNLP_EINVAL, "bad arguments");
+    qlnlp_handle h = first(hh);
+    if (ldz < h->cls.n_nlp) return fail(QLNLP_EINVAL, "ldz < n_nlp");
+    DeviceGuard guard(h->device);
+    if (int rc = ensure_device(h)) return rc;
+    const long long total = (long long)B * h->cls.n_nlp;
+    const int threads = 256;
+    ql::initial_guess_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        base, x0, h->d_x0xf + QL_NX, Z, ldz, B, h->cls.n_nlp, h->cls.k_trans);
+    CUDA_TRY(cudaGetLastError());
+    return QLNLP_OK;
 }
 
 int qlnlp_eval_all(qlnlp_handle h, const double* x, double* f, double* grad, double* g, double* vals)

@@ -644,6 +644,26 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
     }
 }
 
+// Initial guesses of a sweep (main.ipynb:181-196, cell 7): every problem's guess is the class guess `base` except the
+// first 14 states of knots 1..k_trans, which interpolate from the problem's own initial state to the terminal state:
+//   Xguess[k] = xinit + (xterm - xinit) / (k_trans - 1) * (k - 1)          (evaluated left to right, like the notebook)
+// One thread per element of Z; rows of Z are ldz apart.
+__global__ void initial_guess_kernel(const double* __restrict__ base, const double* __restrict__ x0, const double* __restrict__ xterm,
+                                     double* __restrict__ Z, long long ldz, long long B, int n_nlp, int k_trans)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * n_nlp) return;
+    const long long b = t / n_nlp;
+    const int e = (int)(t - b * n_nlp);
+    const int k = e / QL_NZK + 1, i = e - (k - 1) * QL_NZK;
+    double v = __ldg(base + e);
+    if (k <= k_trans && i < QL_NX - 1 && k_trans > 1) {
+        const double xi = __ldg(x0 + b * QL_NX + i);
+        v = __dadd_rn(xi, __dmul_rn(__ddiv_rn(__dsub_rn(__ldg(xterm + i), xi), (double)(k_trans - 1)), (double)(k - 1)));
+    }
+    Z[b * ldz + e] = v;
+}
+
 // DENSE mode (single evaluations): scatter SPARSE_BLOCK values into the zeroed m x n grid
 __global__ void scatter_dense_kernel(const double* __restrict__ vals, const long long* __restrict__ lin,
                                      double* __restrict__ dense, int nnz)

@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "qlnlp_host_pin", "qlnlp_host_unpin", "qlnlp_host_path_info", "qlnlp_host_alloc", "qlnlp_host_free",
     "qlnlp_eval_ragged_classes",
     "qlnlp_hessian_nnz", "qlnlp_hessian_structure", "qlnlp_eval_hessian_lagrangian", "qlnlp_eval_hessian_batch_device",
+    "qlnlp_initial_guess_batch_device",
 )
 _DEBUG_SYMBOLS = ("qlnlp_debug_segments", "qlnlp_debug_vals_map", "qlnlp_debug_build_rows", "qlnlp_debug_host_times")
 
@@ -125,6 +126,7 @@ def load_library(rebuild_if_stale: bool = True):
     L.qlnlp_hessian_structure.argtypes = [vp, vp, vp]
     L.qlnlp_eval_hessian_lagrangian.argtypes = [vp, vp, C.c_double, vp, vp]
     L.qlnlp_eval_hessian_batch_device.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, vp]
+    L.qlnlp_initial_guess_batch_device.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int64, vp]
     L.qlnlp_host_alloc.argtypes = [C.c_int64, C.POINTER(vp)]
     L.qlnlp_host_free.argtypes = [vp, C.c_int64]
     for name in [n for n in EXPORTED_SYMBOLS if n not in ("qlnlp_version", "qlnlp_last_error")] + list(_DEBUG_SYMBOLS):
@@ -517,6 +519,29 @@ class HybridNLP:
 
     def synchronize(self) -> None:
         _check(load_library().qlnlp_synchronize(self._h))
+
+    def initial_guess_batch(self, x0, dt: float = 0.009, out=None, stream=None):
+        """Cell-7 guesses (src/main.ipynb:181-196) for a sweep, built by a CUDA kernel: ``x0`` is a float64 CUDA tensor
+        ``[B, 15]`` of initial states; returns ``Z[B, n_nlp]`` (rows padded to an even length).  Same values, bit for bit,
+        as ``problem.initial_guess_batch`` on the host."""
+        import torch
+        from .problem import initial_guess
+
+        if not (x0.is_cuda and x0.dtype == torch.float64 and x0.dim() == 2 and x0.shape[1] == NX and x0.is_contiguous()):
+            raise ValueError("x0 must be a contiguous float64 CUDA tensor [B, 15]")
+        B = x0.shape[0]
+        key = ("guess_base", float(dt), x0.device.index)
+        base = self._registered.get(key)
+        if base is None:
+            base = torch.from_numpy(initial_guess(self.prob, dt)).to(x0.device)
+            self._registered[key] = base
+        if out is None:
+            out = torch.empty((B, even_ld(self.n_nlp)), dtype=torch.float64, device=x0.device)[:, :self.n_nlp]
+        s = torch.cuda.current_stream(x0.device) if stream is None else stream
+        _check(load_library().qlnlp_initial_guess_batch_device(self._h, B, C.c_void_p(base.data_ptr()), C.c_void_p(x0.data_ptr()),
+                                                               C.c_void_p(out.data_ptr()), out.stride(0) if B > 1 else even_ld(self.n_nlp),
+                                                               C.c_void_p(s.cuda_stream)))
+        return out
 
     def eval_ragged(self, index, flat: Dict[str, "object"], offsets: Dict[str, "object"], *, x0=None, xf=None,
                     stream=None, z_padded: bool = False) -> None:

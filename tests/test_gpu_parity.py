@@ -652,3 +652,22 @@ def test_empty_batches_are_not_an_error(dflt):
     assert out["jac"].shape == (0, nlp.nnz_block) and out["f"].shape == (0,)
     host = nlp.eval_batch_host(np.empty((0, p.n_nlp)))
     assert host["g"].shape == (0, nlp.m_nlp)
+
+
+@pytest.mark.parametrize("N,kt,im", [(61, 21, 1), (31, 11, 2), (33, 33, 1), (5, 2, 2), (2, 2, 1)])
+def test_initial_guess_kernel_matches_the_notebook_formula(N, kt, im):
+    """the sweep's guesses (main.ipynb:181-196) built by a CUDA kernel = the host formula, bit for bit,
+    and the torch variant of problem.initial_guess_batch agrees with both."""
+    p = ql.build_problem(N=N, k_trans=kt, init_mode=im)
+    nlp = ql.HybridNLP.from_problem(p)
+    x0 = ql.sweep_initial_states(p.model, np.linspace(0.25, 3.0, 13), np.linspace(-40.0, -5.0, 11))
+    want = ql.initial_guess_batch(p, x0)
+    x0d = torch.from_numpy(x0).cuda()
+    got = nlp.initial_guess_batch(x0d)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and np.array_equal(got.cpu().numpy(), want)
+    if kt > 1:
+        assert np.array_equal(ql.initial_guess_batch(p, x0d, xp=torch).cpu().numpy(), want)
+    # the guess of the problem's own x0 is the class guess
+    own = nlp.initial_guess_batch(torch.from_numpy(p.x0[None, :].copy()).cuda())
+    assert np.array_equal(own.cpu().numpy()[0], ql.initial_guess(p))
