@@ -54,6 +54,13 @@ enum {
                                      instead of 32,161 at the default instance, same column-major order */
 };
 
+/* OR this into `jac_mode` at qlnlp_create to switch on the kinematic (leg-length) rows the reference carries
+ * COMMENTED OUT (nlp.jl:60,70; constraints.jl:115-138,276-288): cinds[8] = 2 rows per knot, norm(pb - p1) and
+ * norm(pb - p2) with bounds [0, l1 + l2 + lb/2].  m_nlp grows by 2N, every Jacobian pattern by 8N entries (merged
+ * into the column-major order).  Default off = the reference as it runs.  Not available for ragged launches,
+ * registered output rows and the Hessian; this path is not tuned (the Jacobian values take a second pass). */
+#define QLNLP_WITH_KINEMATICS 0x100
+
 /* planar_quadruped.jl:11-20 */
 typedef struct {
     double g, mb, mf, lb, l1, l2;

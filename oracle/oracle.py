@@ -25,7 +25,8 @@ class _Model(C.Structure):
 class _Problem(C.Structure):
     _fields_ = [("N", C.c_int64), ("k_trans", C.c_int64), ("init_mode", C.c_int64),
                 ("model", _Model), ("x0", C.c_double * 15), ("xf", C.c_double * 15),
-                ("Q", C.c_void_p), ("R", C.c_void_p), ("q", C.c_void_p), ("r", C.c_void_p), ("c", C.c_void_p)]
+                ("Q", C.c_void_p), ("R", C.c_void_p), ("q", C.c_void_p), ("r", C.c_void_p), ("c", C.c_void_p),
+                ("kinematics", C.c_int64)]
 
 
 def build(force: bool = False) -> str:
@@ -136,8 +137,11 @@ def rk4_hessian(model, mode: int, x, u, lam) -> np.ndarray:
 class Oracle:
     """CPU evaluator of one problem (same seven entry points as src/moi.jl:1-33)."""
 
-    def __init__(self, prob):
+    def __init__(self, prob, kinematics: bool = False):
+        """``kinematics=True`` switches on the leg-length rows the reference keeps commented out (nlp.jl:60,70;
+        constraints.jl:115-138,276-288): 2N more constraints, 8N more Jacobian entries."""
         self.prob = prob
+        self.kinematics = bool(kinematics)
         self._keep = [_f64(prob.Q), _f64(prob.R), _f64(prob.q), _f64(prob.r), _f64(prob.c)]
         s = _Problem()
         s.N, s.k_trans, s.init_mode = prob.N, prob.k_trans, prob.init_mode
@@ -146,6 +150,7 @@ class Oracle:
             s.x0[i] = float(prob.x0[i])
             s.xf[i] = float(prob.xf[i])
         s.Q, s.R, s.q, s.r, s.c = [a.ctypes.data for a in self._keep]
+        s.kinematics = 1 if kinematics else 0
         self._s = s
         self._p = C.byref(s)
         L = lib()

@@ -148,6 +148,7 @@ typedef struct {
     int64_t N, n_nlp, m_nlp;
     int64_t c_init, c_term, c_dyn, c_cfirst, c_cother, c_fctrl, c_body; /* 0-based block starts */
     int64_t n_cother;
+    int64_t c_kin;            /* first kinematic row (== the reference's m_nlp); 2N rows when switched on */
 } ql_dims;
 
 static ql_dims make_dims(const qlo_problem *p)
@@ -164,6 +165,8 @@ static ql_dims make_dims(const qlo_problem *p)
     d.c_fctrl = d.c_cother + d.n_cother;                   /* 1 row */
     d.c_body = d.c_fctrl + 1;                              /* N rows */
     d.m_nlp = d.c_body + p->N;
+    d.c_kin = d.m_nlp;                                     /* nlp.jl:60 (commented out): 2 rows per knot */
+    if (p->kinematics) d.m_nlp += 2 * p->N;
     return d;
 }
 static inline int64_t xind(int64_t k) { return k * NZK; }        /* 0-based knot k -> first x index */
@@ -317,6 +320,15 @@ static void eval_c_impl(const qlo_problem *p, const double *x0, const double *xf
         const double yb = Z[xind(k) + 1], theta = Z[xind(k) + 2];
         c[d.c_body + k] = yb - p->model.lb / 2 * fabs(sin(theta));
     }
+    /* kinematics_constraints!, constraints.jl:115-138 (commented out upstream; opt-in here):
+     * d[2k-1] = norm(pb - p1), d[2k] = norm(pb - p2); norm of a 2-vector = sqrt(dx*dx + dy*dy) */
+    if (p->kinematics)
+        for (k = 0; k < N; ++k) {
+            const double *x = Z + xind(k);
+            const double d1x = x[0] - x[3], d1y = x[1] - x[4], d2x = x[0] - x[5], d2y = x[1] - x[6];
+            c[d.c_kin + 2 * k] = sqrt(d1x * d1x + d1y * d1y);
+            c[d.c_kin + 2 * k + 1] = sqrt(d2x * d2x + d2y * d2y);
+        }
 }
 
 void qlo_eval_c(const qlo_problem *p, const double *Z, double *c)
@@ -330,6 +342,8 @@ void qlo_constraint_bounds(const qlo_problem *p, double *lb, double *ub)
     int64_t i;
     for (i = 0; i < d.m_nlp; ++i) { lb[i] = 0.0; ub[i] = 0.0; }   /* nlp.jl:66-67 */
     for (i = 0; i < p->N; ++i) ub[d.c_body + i] = INFINITY;       /* nlp.jl:69 */
+    if (p->kinematics)                                            /* nlp.jl:70 (commented out upstream) */
+        for (i = 0; i < 2 * p->N; ++i) ub[d.c_kin + i] = p->model.l1 + p->model.l2 + p->model.lb / 2;
 }
 
 /* moi.jl:51-67, including the "lower bound of F" indices 22/24 + 20(k-1) as written */
@@ -403,6 +417,23 @@ static void jac_c_assign(const qlo_problem *p, const double *Z, put_fn put, void
         else
             put(ctx, d.c_body + k, xind(k) + 2, lb / 2 * cos(theta));
     }
+    /* jac_kinematics, constraints.jl:276-288 (commented out upstream, and written there with the state indices of an
+     * older 10-state model, x[7:8] / x[9:10]; restated with pb = x[1:2], p1 = x[4:5], p2 = x[6:7] as the constraint
+     * itself uses them, :128-134):  d/dpb = d / norm(d),  d/dp_i = -d / norm(d) */
+    if (p->kinematics)
+        for (k = 0; k < N; ++k) {
+            const double *x = Z + xind(k);
+            const double d1x = x[0] - x[3], d1y = x[1] - x[4], d2x = x[0] - x[5], d2y = x[1] - x[6];
+            const double n1 = sqrt(d1x * d1x + d1y * d1y), n2 = sqrt(d2x * d2x + d2y * d2y);
+            put(ctx, d.c_kin + 2 * k, xind(k) + 0, d1x / n1);
+            put(ctx, d.c_kin + 2 * k, xind(k) + 1, d1y / n1);
+            put(ctx, d.c_kin + 2 * k, xind(k) + 3, -d1x / n1);
+            put(ctx, d.c_kin + 2 * k, xind(k) + 4, -d1y / n1);
+            put(ctx, d.c_kin + 2 * k + 1, xind(k) + 0, d2x / n2);
+            put(ctx, d.c_kin + 2 * k + 1, xind(k) + 1, d2y / n2);
+            put(ctx, d.c_kin + 2 * k + 1, xind(k) + 5, -d2x / n2);
+            put(ctx, d.c_kin + 2 * k + 1, xind(k) + 6, -d2y / n2);
+        }
 }
 
 typedef struct { double *jac; int64_t m; } dense_ctx;

@@ -49,6 +49,10 @@ typedef struct {
     double xf[QLO_NX];
     /* per-knot cost, knot-major: Q[k*15+i], R[k*5+i], q[k*15+i], r[k*5+i], c[k]; k = 0..N-1 */
     const double *Q, *R, *q, *r, *c;
+    /* non-zero: the kinematic (leg-length) rows the reference carries COMMENTED OUT are switched on: cinds[8] = 2N rows
+     * d[2k-1] = norm(pb - p1), d[2k] = norm(pb - p2) with bounds [0, l1 + l2 + lb/2] (nlp.jl:60,70; constraints.jl:115-138,
+     * 276-288).  Default 0 = the reference as it runs. */
+    int64_t kinematics;
 } qlo_problem;
 
 int64_t qlo_num_primals(const qlo_problem *p);                 /* nlp.jl:86 */

@@ -21,6 +21,7 @@
 #include "hostrows.h"
 #include "layout.h"
 #include "qlnlp_hess.cuh"
+#include "qlnlp_kin.cuh"
 
 namespace {
 
@@ -145,6 +146,12 @@ struct qlnlp_handle_s {
     double* d_hess_out = nullptr;
     int hess_blocks_per_sm = 0;
     size_t smem_per_sm = 0, smem_optin = 0;
+    // opt-in kinematic rows (qlnlp_kin.cuh): 2N more constraints, 8N more entries in either sparse pattern
+    bool kin = false;
+    double leg_reach = 0;              // l1 + l2 + lb/2
+    std::vector<int32_t> kin_map;      // caller-visible value order of the batch pattern -> scratch position or -(entry + 1)
+    int* d_kin_map = nullptr;
+    std::map<cudaStream_t, std::pair<double*, int64_t>> kin_scratch;   // per stream: reference-order rows (device), capacity
     uint64_t serial = 0;               // unique per handle ever created (addresses get reused)
     std::map<std::vector<uint64_t>, RagTable> rag_tables;       // ragged launches led by this handle (key: the classes' serials)
 
@@ -262,7 +269,10 @@ const void* kernel_fn(int jm, bool fast, bool ragged)
 
 // the sparse pattern batched evaluations of this handle produce (DENSE handles batch in SPARSE_BLOCK)
 int batch_jm(const qlnlp_handle_s* h) { return h->jac_mode == QLNLP_JAC_SPARSE_TRUE ? ql::JM_TRUE : ql::JM_BLOCK; }
-int batch_nnz(const qlnlp_handle_s* h) { return h->jac_mode == QLNLP_JAC_SPARSE_TRUE ? h->cls.nnz_true : h->cls.nnz; }
+int std_nnz(const qlnlp_handle_s* h) { return h->jac_mode == QLNLP_JAC_SPARSE_TRUE ? h->cls.nnz_true : h->cls.nnz; }
+// what the caller sees: the kinematic rows add 8 entries per knot to either pattern and 2 rows per knot to g
+int batch_nnz(const qlnlp_handle_s* h) { return std_nnz(h) + (h->kin ? 8 * h->cls.N : 0); }
+int m_rows(const qlnlp_handle_s* h) { return h->cls.m_nlp + (h->kin ? 2 * h->cls.N : 0); }
 int jm_nnz(const QlClass& c, int jm) { return jm == ql::JM_TRUE ? c.nnz_true : jm == ql::JM_VALS ? c.nnz_vals : c.nnz; }
 
 // SPARSE_TRUE structure (1-based, value order): like sparse_block_structure restricted to structural non-zeros
@@ -510,7 +520,7 @@ int ensure_device(qlnlp_handle h)
     const QlClass& c = h->cls;
     h->ldz_e = (c.n_nlp + 1) & ~1;
     h->ldgrad_e = h->ldz_e;
-    h->ldg_e = (c.m_nlp + 1) & ~1;
+    h->ldg_e = (m_rows(h) + 1) & ~1;
     h->ldjac_e = (batch_nnz(h) + 1) & ~1;
     h->ldv_e = (c.nnz_vals + 1) & ~1;
     // the set-up copies above ran on the legacy default stream and may still be in flight when cudaMemcpy returns
@@ -672,6 +682,83 @@ int ragged_table(const qlnlp_handle* hs, int ncls, const RagTable** out)
     return QLNLP_OK;
 }
 
+// ---- opt-in kinematic rows (qlnlp_kin.cuh) ---------------------------------------------------------------------
+// The caller-visible structure of a handle with kinematic rows: the reference's entries + 8 per knot, column-major.
+// map[o] = position in the reference-order row, or -(8 (k-1) + e + 1) for a kinematic entry.
+void kin_structure(const qlnlp_handle_s* h, std::vector<int64_t>& rows, std::vector<int64_t>& cols, std::vector<int32_t>& map)
+{
+    const QlClass& c = h->cls;
+    const int n0 = std_nnz(h);
+    std::vector<int64_t> r0((size_t)n0), c0((size_t)n0);
+    if (h->jac_mode == QLNLP_JAC_SPARSE_TRUE) sparse_true_structure(c, r0.data(), c0.data());
+    else sparse_block_structure(c, r0.data(), c0.data());
+    struct Ent { int64_t col, row; int32_t src; };
+    std::vector<Ent> all;
+    all.reserve((size_t)n0 + 8 * (size_t)c.N);
+    for (int i = 0; i < n0; ++i) all.push_back({c0[(size_t)i], r0[(size_t)i], i});
+    static const int COL[8] = {0, 1, 3, 4, 0, 1, 5, 6};
+    for (int k = 1; k <= c.N; ++k)
+        for (int e = 0; e < 8; ++e)
+            all.push_back({(int64_t)QL_NZK * (k - 1) + COL[e] + 1, (int64_t)c.m_nlp + 2 * (k - 1) + (e >> 2) + 1, -(8 * (k - 1) + e + 1)});
+    std::sort(all.begin(), all.end(), [](const Ent& a, const Ent& b) { return a.col != b.col ? a.col < b.col : a.row < b.row; });
+    rows.resize(all.size()); cols.resize(all.size()); map.resize(all.size());
+    for (size_t i = 0; i < all.size(); ++i) { rows[i] = all[i].row; cols[i] = all[i].col; map[i] = all[i].src; }
+}
+
+int ensure_kin(qlnlp_handle h)
+{
+    if (h->d_kin_map) return QLNLP_OK;
+    std::vector<int64_t> rows, cols;
+    kin_structure(h, rows, cols, h->kin_map);
+    CUDA_TRY(cudaMalloc(&h->d_kin_map, sizeof(int) * h->kin_map.size()));
+    CUDA_TRY(cudaMemcpy(h->d_kin_map, h->kin_map.data(), sizeof(int) * h->kin_map.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return QLNLP_OK;
+}
+
+// launch() for a handle with kinematic rows: io describes the CALLER's arrays (g rows of m_nlp + 2N, jac rows of
+// nnz + 8N).  The fused kernel writes the reference's g rows in place and its Jacobian values into a scratch row per
+// evaluation; two small kernels append / interleave the kinematic part.
+int launch_kin(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t stream)
+{
+    const QlClass& c = h->cls;
+    if (B == 0) return QLNLP_OK;
+    if (!io || !io->Z) return fail(QLNLP_EINVAL, "io->Z is required");
+    if (io->g && io->ldg < m_rows(h)) return fail(QLNLP_EINVAL, "ldg %lld < m_nlp %d", (long long)io->ldg, m_rows(h));
+    if (io->jac && io->ldjac < batch_nnz(h)) return fail(QLNLP_EINVAL, "ldjac %lld < nnz %d", (long long)io->ldjac, batch_nnz(h));
+    if (int rc = ensure_kin(h)) return rc;
+    qlnlp_batch_io d = *io;
+    const int64_t lds = (std_nnz(h) + 1) & ~1;
+    if (io->jac) {
+        auto& sc = h->kin_scratch[stream];
+        if (sc.second < B * lds) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(stream, &cap);
+            if (cap != cudaStreamCaptureStatusNone) return fail(QLNLP_EINVAL, "kinematic rows: the scratch would have to grow during a graph capture");
+            if (sc.first) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(sc.first); sc.first = nullptr; sc.second = 0; }
+            CUDA_TRY(cudaMalloc(&sc.first, sizeof(double) * (size_t)(B * lds)));
+            sc.second = B * lds;
+        }
+        d.jac = sc.first;
+        d.ldjac = lds;
+    }
+    if (int rc = launch(h, B, &d, stream)) return rc;
+    const int threads = 256;
+    if (io->g) {
+        const long long total = (long long)B * 2 * c.N;
+        ql::kin_g_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(io->Z, io->ldz, io->g, io->ldg, B, c.N, c.m_nlp);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (io->jac) {
+        const int nnz_out = batch_nnz(h);
+        const long long total = (long long)B * nnz_out;
+        ql::kin_expand_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+            h->d_kin_map, nnz_out, d.jac, lds, io->Z, io->ldz, io->jac, io->ldjac, B);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return QLNLP_OK;
+}
+
 // ---- Lagrangian Hessian ----------------------------------------------------------------------------------------
 void hessian_structure(const QlClass& c, int64_t* rows, int64_t* cols)
 {
@@ -804,7 +891,7 @@ int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
     const int nlanes = (int)std::min<int64_t>(MAX_LANES, nchunks);
     for (int l = 0; l < nlanes; ++l)
         if (int rc = reserve_lane(h, h->lanes[l], chunk)) return rc;
-    const bool compact = io->jac && B >= COMPACT_MIN_B;
+    const bool compact = io->jac && B >= COMPACT_MIN_B && !h->kin;      // kinematic rows: the rows come back as they are
     bool touched_only = false;
     if (compact) {
         if (int rc = ensure_plan(h)) return rc;
@@ -817,7 +904,8 @@ int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
     // instead of 50+).  PCIe is what bounds this path, not the kernel: mirror the caller's packing.
     const int64_t ldz_d = (io->ldz == c.n_nlp) ? c.n_nlp : h->ldz_e;
     const int64_t ldgrad_d = (io->grad && io->ldgrad == c.n_nlp) ? c.n_nlp : h->ldgrad_e;
-    const int64_t ldg_d = (io->g && io->ldg == c.m_nlp) ? c.m_nlp : h->ldg_e;
+    const int m_out = m_rows(h);
+    const int64_t ldg_d = (io->g && io->ldg == m_out) ? m_out : h->ldg_e;
     const int64_t ldjac_d = (io->jac && io->ldjac == nnz_b) ? nnz_b : h->ldjac_e;      // uncompacted rows only
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
@@ -839,10 +927,10 @@ int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
         d.grad = io->grad ? ln.grad : nullptr; d.ldgrad = ldgrad_d;
         d.g = io->g ? ln.g : nullptr; d.ldg = ldg_d;
         d.jac = io->jac ? ln.jac : nullptr; d.ldjac = compact ? h->ldv_e : ldjac_d;
-        if (int rc = launch(h, nb, &d, s, compact ? ql::JM_VALS : -1)) return rc;
+        if (int rc = h->kin ? launch_kin(h, nb, &d, s) : launch(h, nb, &d, s, compact ? ql::JM_VALS : -1)) return rc;
         if (io->f) CUDA_TRY(cudaMemcpyAsync(io->f + b0, ln.f, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
         if (io->grad) CUDA_TRY(copy_rows(io->grad + b0 * io->ldgrad, io->ldgrad, ln.grad, ldgrad_d, c.n_nlp, nb, cudaMemcpyDeviceToHost, s));
-        if (io->g) CUDA_TRY(copy_rows(io->g + b0 * io->ldg, io->ldg, ln.g, ldg_d, c.m_nlp, nb, cudaMemcpyDeviceToHost, s));
+        if (io->g) CUDA_TRY(copy_rows(io->g + b0 * io->ldg, io->ldg, ln.g, ldg_d, m_out, nb, cudaMemcpyDeviceToHost, s));
         if (compact) {
             CUDA_TRY(cudaMemcpyAsync(ln.stage, ln.jac, sizeof(double) * nb * h->ldv_e, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaEventRecord(ln.done, s));
@@ -909,7 +997,7 @@ int eval_host(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
     if (!io || !io->Z) return fail(QLNLP_EINVAL, "io->Z is required");
     if (io->ldz < c.n_nlp) return fail(QLNLP_EINVAL, "ldz < n_nlp");
     if (io->grad && io->ldgrad < c.n_nlp) return fail(QLNLP_EINVAL, "ldgrad < n_nlp");
-    if (io->g && io->ldg < c.m_nlp) return fail(QLNLP_EINVAL, "ldg < m_nlp");
+    if (io->g && io->ldg < m_rows(h)) return fail(QLNLP_EINVAL, "ldg < m_nlp");
     if (io->jac && io->ldjac < batch_nnz(h)) return fail(QLNLP_EINVAL, "ldjac < nnz");
     if (io->jac && (reinterpret_cast<uintptr_t>(io->jac) & 7) != 0) return fail(QLNLP_EINVAL, "jac must be 8-byte aligned");
     DeviceGuard guard(h->device);
@@ -994,6 +1082,32 @@ int eval_one(qlnlp_handle hh, const double* x, double* f, double* grad, double* 
     const QlClass& c = h->cls;
     DeviceGuard guard(h->device);
     if (int rc = ensure_device(h)) return rc;
+    if (h->kin) {
+        // kinematic rows: the plain route -- copy x in, evaluate what was asked for, copy it out (no x cache)
+        HostLane& ln = h->lanes[0];
+        if (int rc = reserve_lane(h, ln, 1)) return rc;
+        cudaStream_t s = ln.stream;
+        CUDA_TRY(cudaMemcpyAsync(ln.Z, x, sizeof(double) * c.n_nlp, cudaMemcpyHostToDevice, s));
+        qlnlp_batch_io d;
+        std::memset(&d, 0, sizeof d);
+        d.Z = ln.Z; d.ldz = h->ldz_e;
+        d.f = f ? ln.f : nullptr;
+        d.grad = grad ? ln.grad : nullptr; d.ldgrad = h->ldgrad_e;
+        d.g = g ? ln.g : nullptr; d.ldg = h->ldg_e;
+        d.jac = vals ? ln.jac : nullptr; d.ldjac = h->ldjac_e;
+        int rc = launch_kin(h, 1, &d, s);
+        cudaError_t e = cudaSuccess;
+        if (rc == QLNLP_OK && f) e = cudaMemcpyAsync(f, ln.f, sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (rc == QLNLP_OK && e == cudaSuccess && grad) e = cudaMemcpyAsync(grad, ln.grad, sizeof(double) * c.n_nlp, cudaMemcpyDeviceToHost, s);
+        if (rc == QLNLP_OK && e == cudaSuccess && g) e = cudaMemcpyAsync(g, ln.g, sizeof(double) * m_rows(h), cudaMemcpyDeviceToHost, s);
+        if (rc == QLNLP_OK && e == cudaSuccess && vals) e = cudaMemcpyAsync(vals, ln.jac, sizeof(double) * batch_nnz(h), cudaMemcpyDeviceToHost, s);
+        if (rc == QLNLP_OK && e != cudaSuccess) rc = fail(QLNLP_ECUDA, "single evaluation: %s", cudaGetErrorString(e));
+        const std::string msg = g_err;
+        const cudaError_t es = cudaStreamSynchronize(s);
+        if (rc == QLNLP_OK && es != cudaSuccess) return fail(QLNLP_ECUDA, "single evaluation: %s", cudaGetErrorString(es));
+        g_err = msg;
+        return rc;
+    }
     if (int rc = reserve_one(h)) return rc;
     OneEval& o = h->one;
     const bool hit = h->opt_x_cache && o.valid && std::memcmp(o.hx, x, sizeof(double) * c.n_nlp) == 0;
@@ -1034,14 +1148,16 @@ int eval_dense_jacobian(qlnlp_handle hh, const double* x, double* vals)
     DeviceGuard guard(h->device);
     if (int rc = ensure_device(h)) return rc;
     const QlClass& c = h->cls;
-    const size_t dense_n = (size_t)c.m_nlp * c.n_nlp;
+    const int m = m_rows(h), nz = batch_nnz(h);          // DENSE handles batch in SPARSE_BLOCK (+ the kinematic entries)
+    const size_t dense_n = (size_t)m * c.n_nlp;
     if (!h->d_dense_lin) {
-        std::vector<int64_t> rows(c.nnz), cols(c.nnz);
-        sparse_block_structure(c, rows.data(), cols.data());
-        std::vector<long long> lin(c.nnz);
-        for (int i = 0; i < c.nnz; ++i) lin[i] = (rows[i] - 1) + (long long)c.m_nlp * (cols[i] - 1);
-        CUDA_TRY(cudaMalloc(&h->d_dense_lin, sizeof(long long) * c.nnz));
-        CUDA_TRY(cudaMemcpy(h->d_dense_lin, lin.data(), sizeof(long long) * c.nnz, cudaMemcpyHostToDevice));
+        std::vector<int64_t> rows((size_t)nz), cols((size_t)nz);
+        if (h->kin) { std::vector<int32_t> map; kin_structure(h, rows, cols, map); }
+        else sparse_block_structure(c, rows.data(), cols.data());
+        std::vector<long long> lin((size_t)nz);
+        for (int i = 0; i < nz; ++i) lin[(size_t)i] = (rows[(size_t)i] - 1) + (long long)m * (cols[(size_t)i] - 1);
+        CUDA_TRY(cudaMalloc(&h->d_dense_lin, sizeof(long long) * nz));
+        CUDA_TRY(cudaMemcpy(h->d_dense_lin, lin.data(), sizeof(long long) * nz, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMalloc(&h->d_dense, sizeof(double) * dense_n));
         CUDA_TRY(cudaDeviceSynchronize());     // set-up copy on the default stream before work on the lane's stream
     }
@@ -1053,11 +1169,11 @@ int eval_dense_jacobian(qlnlp_handle hh, const double* x, double* vals)
     std::memset(&d, 0, sizeof d);
     d.Z = ln.Z; d.ldz = h->ldz_e;
     d.jac = ln.jac; d.ldjac = h->ldjac_e;
-    int rc = launch(h, 1, &d, s);
+    int rc = h->kin ? launch_kin(h, 1, &d, s) : launch(h, 1, &d, s);
     if (rc == QLNLP_OK) {
         cudaError_t e = cudaMemsetAsync(h->d_dense, 0, sizeof(double) * dense_n, s);
         if (e == cudaSuccess) {
-            ql::scatter_dense_kernel<<<(c.nnz + 255) / 256, 256, 0, s>>>(ln.jac, h->d_dense_lin, h->d_dense, c.nnz);
+            ql::scatter_dense_kernel<<<(nz + 255) / 256, 256, 0, s>>>(ln.jac, h->d_dense_lin, h->d_dense, nz);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaMemcpyAsync(vals, h->d_dense, sizeof(double) * dense_n, cudaMemcpyDeviceToHost, s);
@@ -1085,6 +1201,8 @@ void destroy_device_state(qlnlp_handle h)
     if (h->one.hx) cudaFreeHost(h->one.hx);
     cudaFree(h->one.dx); cudaFree(h->one.dout);
     cudaFree(h->d_hess_in); cudaFree(h->d_hess_out);
+    cudaFree(h->d_kin_map);
+    for (auto& kv : h->kin_scratch) cudaFree(kv.second.first);
     for (auto& kv : h->rag_tables) cudaFree(kv.second.d_classes);
     cudaFree(h->ticket_pool);
     cudaFree(h->d_cost); cudaFree(h->d_x0xf); cudaFree(h->d_segs); cudaFree(h->d_seg_begin);
@@ -1100,7 +1218,9 @@ int create_one(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_hand
     ql_class_init(&h->cls, (int)d->N, (int)d->k_trans, (int)d->init_mode, d->model.g, d->model.mb, d->model.mf, d->model.lb);
     ql_class_finish(&h->cls);
     h->device = device;
-    h->jac_mode = jac_mode;
+    h->jac_mode = jac_mode & ~QLNLP_WITH_KINEMATICS;
+    h->kin = (jac_mode & QLNLP_WITH_KINEMATICS) != 0;
+    h->leg_reach = d->model.l1 + d->model.l2 + d->model.lb / 2;
     std::memcpy(h->x0, d->x0, sizeof h->x0);
     std::memcpy(h->xf, d->xf, sizeof h->xf);
     const int N = h->cls.N;
@@ -1127,8 +1247,9 @@ int create_one(const qlnlp_problem_desc* d, int device, int jac_mode, qlnlp_hand
     return QLNLP_OK;
 }
 
-int check_desc(const qlnlp_problem_desc* d, int jac_mode)
+int check_desc(const qlnlp_problem_desc* d, int jac_mode_flags)
 {
+    const int jac_mode = jac_mode_flags & ~QLNLP_WITH_KINEMATICS;
     if (d->N < 2 || d->N > QL_MAX_N) return fail(QLNLP_EINVAL, "N=%lld outside [2, 1024]", (long long)d->N);
     if (d->k_trans < 1 || d->k_trans > d->N) return fail(QLNLP_EINVAL, "k_trans=%lld outside [1, N]", (long long)d->k_trans);
     if (d->init_mode != 1 && d->init_mode != 2) return fail(QLNLP_EINVAL, "init_mode must be 1 or 2");
@@ -1192,9 +1313,9 @@ int qlnlp_dims(qlnlp_handle h, int64_t* n_nlp, int64_t* m_nlp, int64_t* nnz, int
 {
     if (int rc = check_handle(h)) return rc;
     if (n_nlp) *n_nlp = h->cls.n_nlp;
-    if (m_nlp) *m_nlp = h->cls.m_nlp;
-    if (nnz) *nnz = (h->jac_mode == QLNLP_JAC_DENSE) ? (int64_t)h->cls.m_nlp * h->cls.n_nlp : batch_nnz(h);
-    if (nnz_block) *nnz_block = h->cls.nnz;
+    if (m_nlp) *m_nlp = m_rows(h);
+    if (nnz) *nnz = (h->jac_mode == QLNLP_JAC_DENSE) ? (int64_t)m_rows(h) * h->cls.n_nlp : batch_nnz(h);
+    if (nnz_block) *nnz_block = h->cls.nnz + (h->kin ? 8 * h->cls.N : 0);
     return QLNLP_OK;
 }
 
@@ -1223,7 +1344,13 @@ int qlnlp_jacobian_structure(qlnlp_handle h, int64_t* rows, int64_t* cols)
         // vec(Tuple.(CartesianIndices(zeros(m, n)))): column-major, row fastest (moi.jl:31-33)
         int64_t n = 0;
         for (int64_t col = 1; col <= h->cls.n_nlp; ++col)
-            for (int64_t row = 1; row <= h->cls.m_nlp; ++row) { rows[n] = row; cols[n] = col; ++n; }
+            for (int64_t row = 1; row <= m_rows(h); ++row) { rows[n] = row; cols[n] = col; ++n; }
+    } else if (h->kin) {
+        std::vector<int64_t> r, c;
+        std::vector<int32_t> map;
+        kin_structure(h, r, c, map);
+        std::copy(r.begin(), r.end(), rows);
+        std::copy(c.begin(), c.end(), cols);
     } else if (h->jac_mode == QLNLP_JAC_SPARSE_TRUE) {
         sparse_true_structure(h->cls, rows, cols);
     } else {
@@ -1236,8 +1363,10 @@ int qlnlp_constraint_bounds(qlnlp_handle h, double* lb, double* ub)
 {
     if (int rc = check_handle(h)) return rc;
     if (!lb || !ub) return fail(QLNLP_EINVAL, "null output");
-    for (int i = 0; i < h->cls.m_nlp; ++i) { lb[i] = 0.0; ub[i] = 0.0; }         // nlp.jl:66-67
+    for (int i = 0; i < m_rows(h); ++i) { lb[i] = 0.0; ub[i] = 0.0; }            // nlp.jl:66-67
     for (int i = 0; i < h->cls.N; ++i) ub[h->cls.c_body + i] = INFINITY;          // nlp.jl:69
+    if (h->kin)                                                                   // nlp.jl:70 (commented out upstream)
+        for (int i = 0; i < 2 * h->cls.N; ++i) ub[h->cls.m_nlp + i] = h->leg_reach;
     return QLNLP_OK;
 }
 
@@ -1287,6 +1416,7 @@ int qlnlp_eval_batch_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io,
     if (B == 0) return QLNLP_OK;
     DeviceGuard guard(h->device);
     if (int rc = ensure_device(h)) return rc;
+    if (h->kin) return launch_kin(h, B, io, static_cast<cudaStream_t>(stream));
     return launch(h, B, io, static_cast<cudaStream_t>(stream));
 }
 
@@ -1300,7 +1430,8 @@ int qlnlp_eval_batch_device_multi(qlnlp_handle h, const int64_t* B, const qlnlp_
         if (B[i] == 0) continue;
         DeviceGuard guard(s->device);
         if (int rc = ensure_device(s)) return rc;
-        if (int rc = launch(s, B[i], io + i, streams ? static_cast<cudaStream_t>(streams[i]) : nullptr)) return rc;
+        cudaStream_t st = streams ? static_cast<cudaStream_t>(streams[i]) : nullptr;
+        if (int rc = s->kin ? launch_kin(s, B[i], io + i, st) : launch(s, B[i], io + i, st)) return rc;
     }
     return QLNLP_OK;
 }
@@ -1323,6 +1454,7 @@ int qlnlp_eval_ragged_device(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io
     if (int rc = check_handle(h)) return rc;
     if (!h->subs.empty()) return fail(QLNLP_EINVAL, "multi-device handle: ragged launches take a single-device handle");
     if (!rg) return fail(QLNLP_EINVAL, "null ragged descriptor");
+    if (h->kin) return fail(QLNLP_EINVAL, "ragged launches do not carry the kinematic rows");
     if (B == 0) return QLNLP_OK;
     DeviceGuard guard(h->device);
     if (int rc = ensure_device(h)) return rc;
@@ -1342,6 +1474,7 @@ int qlnlp_eval_ragged_classes(const qlnlp_handle* hs, int ncls, int64_t B, const
         if (!hs[i]->subs.empty()) return fail(QLNLP_EINVAL, "multi-device handle: ragged launches take single-device handles");
         if (hs[i]->device != hs[0]->device) return fail(QLNLP_EINVAL, "the classes of a ragged launch must share one device");
         if (batch_jm(hs[i]) != batch_jm(hs[0])) return fail(QLNLP_EINVAL, "the classes of a ragged launch must share one Jacobian pattern");
+        if (hs[i]->kin) return fail(QLNLP_EINVAL, "ragged launches do not carry the kinematic rows");
     }
     if (B == 0) return QLNLP_OK;
     DeviceGuard guard(hs[0]->device);
@@ -1385,6 +1518,7 @@ int qlnlp_host_output_register(qlnlp_handle h, double* jac, int64_t ldjac, int64
     if (!jac || B < 1) return fail(QLNLP_EINVAL, "bad buffer");
     if ((reinterpret_cast<uintptr_t>(jac) & 7) != 0) return fail(QLNLP_EINVAL, "jac must be 8-byte aligned");
     if (ldjac < batch_nnz(h)) return fail(QLNLP_EINVAL, "ldjac < nnz");
+    if (h->kin) return fail(QLNLP_EINVAL, "registered output rows are not available with the kinematic rows");
     const int n = h->subs.empty() ? 1 : (int)h->subs.size();
     // every device's handle may be asked for any slice of the buffer: all of them learn the registration; the
     // constant image is written once, by the first handle's pool
@@ -1495,6 +1629,7 @@ int qlnlp_eval_hessian_batch_device(qlnlp_handle h, int64_t B, const double* Z, 
 {
     if (int rc = check_handle(h)) return rc;
     if (!h->subs.empty()) return fail(QLNLP_EINVAL, "multi-device handle: the Hessian takes a single-device handle");
+    if (h->kin) return fail(QLNLP_EINVAL, "the Hessian does not cover the kinematic rows");
     if (B == 0) return QLNLP_OK;
     DeviceGuard guard(h->device);
     if (int rc = ensure_device(h)) return rc;
@@ -1505,6 +1640,7 @@ int qlnlp_eval_hessian_lagrangian(qlnlp_handle hh, const double* x, double sigma
 {
     if (int rc = check_handle(hh)) return rc;
     if (!x || !lambda || !vals) return fail(QLNLP_EINVAL, "null argument");
+    if (hh->kin) return fail(QLNLP_EINVAL, "the Hessian does not cover the kinematic rows");
     qlnlp_handle h = first(hh);
     const QlClass& c = h->cls;
     DeviceGuard guard(h->device);

@@ -24,6 +24,7 @@ from .problem import NX, NU, PlanarQuadruped, ProblemData, QuadraticCost, packZ 
 
 QLNLP_OK, QLNLP_EINVAL, QLNLP_ENODEVICE, QLNLP_ECUDA, QLNLP_ENOMEM = range(5)
 JAC_SPARSE_BLOCK, JAC_DENSE, JAC_SPARSE_TRUE = 0, 1, 2
+WITH_KINEMATICS = 0x100
 
 # every symbol include/qlnlp.h declares
 EXPORTED_SYMBOLS = (
@@ -201,26 +202,28 @@ class HybridNLP:
     def __init__(self, model: PlanarQuadruped, obj: Sequence[QuadraticCost], init_mode: int, k_trans: int,
                  N: int, x0, xf, integration: str = "RK4", *, use_sparse_jacobian: bool = False,
                  pattern: str = "block", device: int = 0, devices: Optional[Sequence[int]] = None,
-                 hessian: bool = False):
+                 hessian: bool = False, kinematics: bool = False):
         if integration != "RK4":
             raise ValueError("only RK4 is implemented (as in the reference)")
         self._init(ProblemData.from_costs(model, obj, init_mode, k_trans, N, x0, xf), use_sparse_jacobian, device, pattern,
-                   devices)
+                   devices, kinematics)
         self.hessian = bool(hessian)
 
     @classmethod
     def from_problem(cls, prob: ProblemData, *, use_sparse_jacobian: bool = True, pattern: str = "block",
-                     device: int = 0, devices: Optional[Sequence[int]] = None, hessian: bool = False) -> "HybridNLP":
+                     device: int = 0, devices: Optional[Sequence[int]] = None, hessian: bool = False,
+                     kinematics: bool = False) -> "HybridNLP":
         """``devices=[0, 1, ...]`` builds a multi-device evaluator (``qlnlp_create_multi``): host-pointer batches are
         sharded over the listed GPUs by the library, ``eval_batch_multi`` launches one shard per device.
-        ``hessian=True`` advertises ``"Hess"`` (the reference does not, src/moi.jl:26-28)."""
+        ``hessian=True`` advertises ``"Hess"`` (the reference does not, src/moi.jl:26-28).  ``kinematics=True`` switches
+        on the leg-length rows the reference keeps commented out (nlp.jl:60,70; constraints.jl:115-138,276-288)."""
         self = cls.__new__(cls)
-        self._init(prob, use_sparse_jacobian, device, pattern, devices)
+        self._init(prob, use_sparse_jacobian, device, pattern, devices, kinematics)
         self.hessian = bool(hessian)
         return self
 
     def _init(self, prob: ProblemData, use_sparse_jacobian: bool, device: int, pattern: str = "block",
-              devices: Optional[Sequence[int]] = None):
+              devices: Optional[Sequence[int]] = None, kinematics: bool = False):
         if pattern not in ("block", "true"):
             raise ValueError("pattern must be 'block' or 'true'")
         self.pattern = pattern
@@ -244,11 +247,13 @@ class HybridNLP:
         d.Q, d.R, d.q, d.r, d.c = (a.ctypes.data for a in (prob.Q, prob.R, prob.q, prob.r, prob.c))
         self._h = C.c_void_p()
         mode = JAC_DENSE if not use_sparse_jacobian else (JAC_SPARSE_TRUE if pattern == "true" else JAC_SPARSE_BLOCK)
+        self.kinematics = bool(kinematics)
+        flags = mode | (WITH_KINEMATICS if kinematics else 0)
         if devices is None:
-            _check(L.qlnlp_create(C.byref(d), self.device, mode, C.byref(self._h)))
+            _check(L.qlnlp_create(C.byref(d), self.device, flags, C.byref(self._h)))
         else:
             arr = (C.c_int * len(self.devices))(*self.devices)
-            _check(L.qlnlp_create_multi(C.byref(d), arr, len(self.devices), mode, C.byref(self._h)))
+            _check(L.qlnlp_create_multi(C.byref(d), arr, len(self.devices), flags, C.byref(self._h)))
         self._registered = {}
         self.hessian = False
         nh = C.c_int64()
@@ -265,6 +270,8 @@ class HybridNLP:
         N, kt = self.N, self.k_trans
         ends = np.cumsum([NX, NX - 1, (N - 1) * NX, N, N - kt + 1, 1, N])
         self.cinds = [range(int(e - w) + 1, int(e) + 1) for e, w in zip(ends, [NX, NX - 1, (N - 1) * NX, N, N - kt + 1, 1, N])]
+        if kinematics:                                    # nlp.jl:60 (commented out upstream): cinds[8]
+            self.cinds.append(range(int(ends[-1]) + 1, int(ends[-1]) + 2 * N + 1))
         self.lb, self.ub = self.constraint_bounds()
         self.zL = np.full(self.n_nlp, -np.inf)           # nlp.jl:73-74
         self.zU = np.full(self.n_nlp, np.inf)

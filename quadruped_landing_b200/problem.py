@@ -247,7 +247,9 @@ def sweep_initial_states(model: PlanarQuadruped, h_drops, theta0_degs) -> np.nda
 
 def initial_guess_batch(prob: ProblemData, x0_batch, dt: float = 0.009, xp=np):
     """Cell-7 guess (main.ipynb:181-196) for many initial states at once.  ``xp`` is numpy or torch: with torch
-    tensors on the GPU the guesses are built on the device, so a sweep needs no host-to-device traffic."""
+    tensors on the GPU the guesses are built on the device by eager tensor operations (equal to the host formula to
+    1 ulp: torch divides by a scalar through its reciprocal).  ``HybridNLP.initial_guess_batch`` does the same with a
+    CUDA kernel and reproduces the host formula bit for bit."""
     N, kt = prob.N, prob.k_trans
     base = initial_guess(prob, dt)                       # the class guess: everything that does not depend on x0
     if xp is np:

@@ -667,7 +667,10 @@ def test_initial_guess_kernel_matches_the_notebook_formula(N, kt, im):
     torch.cuda.synchronize()
     assert got.shape == want.shape and np.array_equal(got.cpu().numpy(), want)
     if kt > 1:
-        assert np.array_equal(ql.initial_guess_batch(p, x0d, xp=torch).cpu().numpy(), want)
+        # the eager-torch variant of problem.initial_guess_batch divides by multiplying with a reciprocal on the GPU:
+        # equal to 1 ulp, not to the bit (the kernel above is the exact one)
+        eager = ql.initial_guess_batch(p, x0d, xp=torch).cpu().numpy()
+        assert np.abs(eager - want).max() <= 4 * np.finfo(np.float64).eps * max(1.0, np.abs(want).max())
     # the guess of the problem's own x0 is the class guess
     own = nlp.initial_guess_batch(torch.from_numpy(p.x0[None, :].copy()).cuda())
     assert np.array_equal(own.cpu().numpy()[0], ql.initial_guess(p))
