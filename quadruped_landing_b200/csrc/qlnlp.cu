@@ -14,6 +14,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -435,6 +436,8 @@ int ensure_pool(qlnlp_handle h)
 int set_carveout(const void* fn, int resident_blocks, size_t smem_per_block, size_t smem_per_sm)
 {
     static std::map<const void*, size_t> g_need;
+    static std::mutex g_mu;                    // the devices of a multi-device handle are set up from their driver threads
+    std::lock_guard<std::mutex> lk(g_mu);
     size_t& need = g_need[fn];
     need = std::max(need, (size_t)resident_blocks * (smem_per_block + 1024));
     const int pct = (int)std::min<size_t>(100, need * 100 / std::max<size_t>(1, smem_per_sm) + 2);
