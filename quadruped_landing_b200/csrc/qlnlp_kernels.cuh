@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
         for (int i = lane; i < P.nseg; i += QL_LANES) dst[i] = __ldg(src + i);
     }
 
-    for (; b < P.B; b = nb) {
+    while (b < P.B) {
         if (zbulk) { mbar_wait(mbar, zphase); zphase ^= 1u; }
         else cp_async_wait_all();
         __syncwarp();
@@ -438,12 +438,14 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
                 __syncwarp();
                 const int nact = min(QL_LANES, c.N - p * QL_LANES);
                 const double2* f2 = reinterpret_cast<const double2*>(fbuf);
-                int s = 0;
-                for (; s + 1 < nact; s += 2) {
-                    const double2 t = f2[s >> 1];
-                    fsum = __dadd_rn(__dadd_rn(fsum, t.x), t.y);
+                double2 tv[QL_LANES / 2];           // all loads first (their latencies overlap), then the dependent chain
+#pragma unroll
+                for (int s = 0; s < QL_LANES / 2; ++s) tv[s] = f2[s];
+#pragma unroll
+                for (int s = 0; s < QL_LANES / 2; ++s) {
+                    if (2 * s < nact) fsum = __dadd_rn(fsum, tv[s].x);
+                    if (2 * s + 1 < nact) fsum = __dadd_rn(fsum, tv[s].y);
                 }
-                if (s < nact) fsum = __dadd_rn(fsum, fbuf[s]);
                 __syncwarp();
             }
 
@@ -632,6 +634,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
 
         // ---- 6. cost (accumulated in the reference's order above)
         if (P.f && lane == 0) P.f[pi] = fsum;
+        b = nb;
     }
     if (WITH_JAC && P.bulk && lane == 0) bulk_wait_all();
     // the last CTA to leave re-arms the counters for the next launch on this stream
