@@ -594,7 +594,11 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
         per_sm = std::min(per_sm, (want_cost && short_batch) ? 6 : 5);
     }
     const int64_t resident = (int64_t)h->sm_count * per_sm;
-    const int grid = (int)std::min<int64_t>(B, resident);
+    int grid = (int)std::min<int64_t>(B, resident);
+    if (const char* e = std::getenv("QLNLP_GRID")) {                 // experiment knob: explicit grid size
+        const int gsz = std::atoi(e);
+        if (gsz >= 1 && gsz <= resident) grid = (int)std::min<int64_t>(B, gsz);
+    }
     // work counter of this stream (launches on one stream are ordered, so they can share it; the kernel's last CTA
     // re-arms it).  Concurrent launches of the handle on different streams get different counters.
     auto it = h->tickets.find(stream);
