@@ -1814,9 +1814,16 @@ int qlnlp_debug_build_rows(qlnlp_handle h, const double* vals, int64_t ldv, doub
     qlnlp_handle s = first(h);
     if (int rc = ensure_plan(s)) return rc;
     if (threads == 1) { s->plan->build_rows(vals, ldv, jac, ldjac, 0, rows, touched_only != 0); return QLNLP_OK; }
+    const bool async = threads < -1;           // negative: the workers-only path the host pipeline uses (Pool::start)
+    if (async) threads = -threads;
     if (threads > 1) { s->opt_host_threads = threads; s->pool.reset(); }
     if (int rc = ensure_pool(s)) return rc;
-    s->plan->build(s->pool.get(), vals, ldv, jac, ldjac, rows, touched_only != 0);
+    if (async) {
+        s->plan->build_async(s->pool.get(), vals, ldv, jac, ldjac, rows, touched_only != 0);
+        s->pool->finish();
+    } else {
+        s->plan->build(s->pool.get(), vals, ldv, jac, ldjac, rows, touched_only != 0);
+    }
     return QLNLP_OK;
 }
 

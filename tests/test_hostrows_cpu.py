@@ -81,7 +81,7 @@ def test_pool_builds_the_same_rows():
     B = 97
     rows = o.eval_batch(_batch(prob, B, 3), want=("jac",))["jac"]
     vals = np.ascontiguousarray(rows[:, nlp._debug_vals_map()])
-    for threads in (2, 5):
+    for threads in (2, 5, -2, -4):            # negative: workers only, asynchronously (what the host pipeline does)
         out = np.full((B, nlp.nnz_batch), np.nan)
         for _ in range(3):                       # back-to-back jobs on the persistent pool
             nlp._debug_build_rows(vals, out, touched_only=False, threads=threads)
