@@ -50,6 +50,13 @@ class _Callbacks:
         self._grad = np.empty(nlp.n_nlp)
         self._g = np.empty(nlp.m_nlp)
         self._vals = np.empty(nlp.nnz)
+        # exact Lagrangian Hessian when the evaluator offers :Hess (not in the reference, moi.jl:26-28)
+        self.has_hess = "Hess" in (nlp.features_available() if hasattr(nlp, "features_available") else ())
+        if self.has_hess:
+            self.n["hess"] = 0
+            hr, hc = nlp.hessian_structure_arrays()
+            self.hrows, self.hcols = hr - 1, hc - 1
+            self._h = np.empty(len(hr))
 
     def f(self, x):
         self.n["f"] += 1
@@ -69,6 +76,18 @@ class _Callbacks:
         self.n["jac"] += 1
         self.nlp.eval_constraint_jacobian(self._vals, x)
         return self._sp.csr_matrix((self._vals, (self.rows, self.cols)), shape=(self.nlp.m_nlp, self.nlp.n_nlp))
+
+
+    def hess_values(self, x, sigma, lam):
+        self.n["hess"] += 1
+        self.nlp.eval_hessian_lagrangian(self._h, x, sigma, lam)
+        return self._h
+
+    def hess_matrix(self, x, sigma, lam):
+        """sigma Hess f + sum lam_r Hess g_r as a symmetric sparse matrix (the evaluator reports the lower triangle)"""
+        v = self.hess_values(x, sigma, lam)
+        L = self._sp.csr_matrix((v, (self.hrows, self.hcols)), shape=(self.nlp.n_nlp, self.nlp.n_nlp))
+        return L + self._sp.tril(L, -1).T
 
 
 def solve(x0, nlp: HybridNLP, *, tol: float = 1.0e-6, c_tol: float = 1.0e-6, max_iter: int = 2000,
@@ -106,11 +125,15 @@ def solve(x0, nlp: HybridNLP, *, tol: float = 1.0e-6, c_tol: float = 1.0e-6, max
                 nlp.eval_constraint_jacobian(cb._vals, x)
                 return cb._vals.copy()
 
+        if cb.has_hess:
+            _P.hessianstructure = staticmethod(lambda: (cb.hrows, cb.hcols))
+            _P.hessian = staticmethod(lambda x, lagrange, obj_factor: cb.hess_values(x, obj_factor, lagrange).copy())
         prob = cyipopt.Problem(n=nlp.n_nlp, m=nlp.m_nlp, problem_obj=_P(), lb=xl, ub=xu, cl=cl, cu=cu)
         prob.add_option("max_iter", int(max_iter))            # moi.jl:78-80
         prob.add_option("tol", float(tol))
         prob.add_option("constr_viol_tol", float(c_tol))
-        prob.add_option("hessian_approximation", "limited-memory")   # no :Hess feature (moi.jl:26-28)
+        if not cb.has_hess:
+            prob.add_option("hessian_approximation", "limited-memory")   # no :Hess feature (moi.jl:26-28)
         prob.add_option("print_level", 5 if verbose else 0)
         x, info = prob.solve(x0)
         g = cb.g(x)
@@ -121,8 +144,14 @@ def solve(x0, nlp: HybridNLP, *, tol: float = 1.0e-6, c_tol: float = 1.0e-6, max
         raise ValueError(f"unknown backend {backend!r}")
     from scipy.optimize import Bounds, NonlinearConstraint, minimize, BFGS
 
-    con = NonlinearConstraint(cb.g, cl, cu, jac=cb.jac, hess=BFGS())     # quasi-Newton: the evaluator has no Hessian
-    res = minimize(cb.f, x0, jac=cb.grad, hess=BFGS(), method="trust-constr", bounds=Bounds(xl, xu, keep_feasible=False),
+    if cb.has_hess:       # exact second derivatives: sigma = 1, lambda = 0 for the objective; sigma = 0, lambda = v for g
+        zero = np.zeros(nlp.m_nlp)
+        con = NonlinearConstraint(cb.g, cl, cu, jac=cb.jac, hess=lambda x, v: cb.hess_matrix(x, 0.0, v))
+        fhess = lambda x: cb.hess_matrix(x, 1.0, zero)
+    else:
+        con = NonlinearConstraint(cb.g, cl, cu, jac=cb.jac, hess=BFGS())     # quasi-Newton: the evaluator has no Hessian
+        fhess = BFGS()
+    res = minimize(cb.f, x0, jac=cb.grad, hess=fhess, method="trust-constr", bounds=Bounds(xl, xu, keep_feasible=False),
                    constraints=[con],
                    options={"maxiter": int(max_iter), "gtol": float(tol), "xtol": 1e-12, "verbose": int(verbose),
                             "sparse_jacobian": True, "initial_constr_penalty": 1.0})

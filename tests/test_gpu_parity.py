@@ -485,6 +485,18 @@ def test_solver_loop_on_the_gpu_evaluator():
     assert_same_bits(nlp, {"jac": vals}, {"jac": o.jac_c_sparse_true(res.x)})
 
 
+def test_solver_loop_with_the_exact_hessian():
+    """The same glue with :Hess switched on: the solver receives sigma Hess f + sum lam Hess g from the GPU."""
+    import warnings
+    from quadruped_landing_b200.solve import solve
+    p = ql.build_problem(N=9, k_trans=4)
+    nlp = ql.HybridNLP.from_problem(p, pattern="true", hessian=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = solve(ql.initial_guess(p), nlp, tol=1e-3, c_tol=1e-3, max_iter=5, backend="trust-constr")
+    assert res.evals["hess"] >= 2 and np.isfinite(res.objective)
+
+
 def test_randomised_stress_against_the_oracle():
     """tests/fuzz_gpu.py for 20 s: random classes (N in 2..121, any k_trans / init_mode), batch sizes 1..3000,
     paddings and alignments, output subsets, both sparse patterns, device and host entry points, canary rows.

@@ -29,6 +29,18 @@ def test_solve_drives_the_four_callbacks_through_a_solver_loop():
     assert np.all(res.x >= xl - 1e-6) and np.all(res.x <= xu + 1e-6)      # bounds of moi.jl:51-67 are honoured
 
 
+def test_solve_uses_the_exact_hessian_when_offered():
+    """With :Hess on the glue hands the solver exact second derivatives instead of BFGS updates:
+    sigma = 1, lambda = 0 for the objective, sigma = 0, lambda = v for the constraints."""
+    import warnings
+    p = ql.build_problem(N=7, k_trans=3)
+    nlp = OracleNLP(p, hessian=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = solve(ql.initial_guess(p), nlp, tol=1e-3, c_tol=1e-3, max_iter=8, backend="trust-constr")
+    assert res.evals["hess"] >= 2 and 1 <= res.iterations <= 8 and np.isfinite(res.objective)
+
+
 def test_solve_requires_a_sparse_structure():
     class Dense(OracleNLP):
         use_sparse_jacobian = False
