@@ -230,6 +230,18 @@ __device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigne
     }
 }
 
+// fsum + t[0] + t[1] + ... + t[31], strictly left to right (costs.jl:9-15); lanes without a knot have stored -0.0
+__device__ __forceinline__ double f_chain(double fsum, const double* fbuf)
+{
+    const double2* f2 = reinterpret_cast<const double2*>(fbuf);
+#pragma unroll
+    for (int s = 0; s < QL_LANES / 2; ++s) {
+        const double2 t = f2[s];
+        fsum = __dadd_rn(__dadd_rn(fsum, t.x), t.y);
+    }
+    return fsum;
+}
+
 template <int JM, bool FASTDIV, bool RAGGED>
 __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM == JM_BLOCK ? 8 : QL_TRUE_WARPS)) eval_kernel(const __grid_constant__ Launch P)
 {
@@ -284,11 +296,13 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
     // warp is free.  Besides balancing the load this keeps the rows being written at any moment within a narrow,
     // advancing address window, which the memory system likes much better than the drifting round-robin pattern of a
     // static assignment (+5 % full / +10 % g+J throughput at B=65,536, profiles/r01_ablation.md section 7).
-    auto take = [&]() -> long long {
+    auto take_issue = [&]() -> unsigned {             // lane 0 draws the ticket; nothing waits for the atomic yet
         unsigned t = 0;
         if (lane == 0) t = atomicAdd(P.ticket, 1u);
-        return (long long)__shfl_sync(0xffffffffu, t, 0);
+        return t;
     };
+    auto take_get = [&](unsigned t) -> long long { return (long long)__shfl_sync(0xffffffffu, t, 0); };
+    auto take = [&]() -> long long { return take_get(take_issue()); };
     long long b = take();
     long long nb = P.B;
     if (b < P.B) stage_z(zrow_of(b), zaddr, mbar, n_of(b), lane, zbulk);
@@ -306,14 +320,13 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
         double fsum = 0.0;
         // the kernels without the SPARSE_BLOCK stream are latency-bound: take the next ticket now, so that the atomic's
         // round trip is hidden behind this evaluation (the SPARSE_BLOCK kernel has no register to spare for it)
-        if (JM != JM_BLOCK) {
-            nb = take();
-#ifndef QL_NO_L2_PREFETCH
-            // (measured: +13 % with the cost/gradient part in the evaluation, -17 % for the short g-only evaluation,
-            // where the prefetch is still in flight when the load itself is issued; profiles/r02_kernel_ab.md)
-            if (zbulk && (P.f || P.grad) && nb < P.B && lane == 0) prefetch_l2(zrow_of(nb), 8u * (unsigned)(n_of(nb) + 1));
-#endif
-        }
+        // With a cost / gradient part the ticket is only drawn here and read after the first pass's cost section, when
+        // the atomic has returned.  The short g-only evaluation reads it at once: reading it late made that launch
+        // bimodal (265 or 349 M evals/s from one process to the next, profiles/r02_kernel_ab.md), at once it is steady.
+        const bool late_ticket = JM != JM_BLOCK && (P.f || P.grad);
+        unsigned tkt = 0;
+        if (JM != JM_BLOCK) tkt = take_issue();
+        if (JM != JM_BLOCK && !late_ticket) nb = take_get(tkt);
         const long long pi = (RAGGED && P.index) ? __ldg(P.index + b) : b;      // problem number (f, x0, xf, offsets)
         if (RAGGED) {
             const int cid = P.cls_of ? __ldg(P.cls_of + pi) : 0;
@@ -359,6 +372,9 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
             const bool has_u = k < c.N;
             const bool jump = has_u && (k == c.k_trans - 1);   // constraints.jl:29 / :190
             double* const zk = zbuf + (k - 1) * QL_NZK;
+            // costs.jl:9-15 accumulates J knot by knot: the 32 terms of the PREVIOUS pass are added here, in order,
+            // where few registers are live (every lane adds up the same sequence; only lane 0's copy is stored)
+            if (P.f && p > 0) fsum = f_chain(fsum, fbuf);
 
             // ---- 1. my knot's slice of Z: x_k, u_k, x_{k+1} = zk[0..34], fetched with 128-bit shared loads (the knot
             // stride of 160 B makes 64-bit loads 4-way bank conflicted; 16-byte loads halve the wavefronts)
@@ -380,7 +396,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
             __syncwarp();       // every lane holds its inputs: this pass's slice of zbuf may be overwritten
 
             // ---- 2. cost and gradient (costs.jl:6-34, quadratic_cost.jl:44-52); gradient in place over Z
-            double lane_term = 0.0;
+            double lane_term = -0.0;                // lanes without a knot add -0.0: x + (-0.0) == x bit for bit
             if (act && (P.f || gradrow)) {
                 const double* ct = cost + (k - 1);
                 const int np = npad;
@@ -432,21 +448,17 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
                 lane_term = term;
             }
             if (P.f) {
-                // costs.jl:9-15 accumulates J knot by knot: do the same, through shared memory (every lane adds up
-                // the same sequence; only lane 0's copy is stored)
-                fbuf[lane] = lane_term;
-                __syncwarp();
-                const int nact = min(QL_LANES, c.N - p * QL_LANES);
-                const double2* f2 = reinterpret_cast<const double2*>(fbuf);
-                double2 tv[QL_LANES / 2];           // all loads first (their latencies overlap), then the dependent chain
-#pragma unroll
-                for (int s = 0; s < QL_LANES / 2; ++s) tv[s] = f2[s];
-#pragma unroll
-                for (int s = 0; s < QL_LANES / 2; ++s) {
-                    if (2 * s < nact) fsum = __dadd_rn(fsum, tv[s].x);
-                    if (2 * s + 1 < nact) fsum = __dadd_rn(fsum, tv[s].y);
-                }
-                __syncwarp();
+                __syncwarp();                       // the previous pass's terms have been read by every lane
+                fbuf[lane] = lane_term;             // read back in the next pass, or after the last one (below)
+            }
+            if (late_ticket && p == 0) {
+                nb = take_get(tkt);
+#ifndef QL_NO_L2_PREFETCH
+                // (measured: +13 % with the cost/gradient part in the evaluation, -17 % for the short g-only
+                // evaluation, where the prefetch is still in flight when the load itself is issued;
+                // profiles/r02_kernel_ab.md)
+                if (zbulk && nb < P.B && lane == 0) prefetch_l2(zrow_of(nb), 8u * (unsigned)(n_of(nb) + 1));
+#endif
             }
 
             // flush this pass's gradient slice with coalesced stores; the slice is then free for the defects
@@ -458,6 +470,8 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
                 if ((reinterpret_cast<uintptr_t>(gradrow) & 15) == 0) {      // e0 is even: 16-byte stores
                     const double2* s2 = reinterpret_cast<const double2*>(slice);
                     double2* d2 = reinterpret_cast<double2*>(gradrow + e0);
+                    // (one load, one store at a time on purpose: batching the loads ahead of the stores measured 8 % slower,
+                    // profiles/r02_kernel_ab.md)
                     for (int i = lane; i < (cnt >> 1); i += QL_LANES) QL_GST(d2 + i, s2[i]);
                     if ((cnt & 1) && lane == 0) QL_GST(gradrow + e0 + cnt - 1, slice[cnt - 1]);
                 } else {
@@ -633,7 +647,10 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
         }
 
         // ---- 6. cost (accumulated in the reference's order above)
-        if (P.f && lane == 0) P.f[pi] = fsum;
+        if (P.f) {
+            fsum = f_chain(fsum, fbuf);          // the last pass's terms
+            if (lane == 0) P.f[pi] = fsum;
+        }
         b = nb;
     }
     if (WITH_JAC && P.bulk && lane == 0) bulk_wait_all();

@@ -17,17 +17,20 @@ sys.path.insert(0, %r)
 import numpy as np, torch
 import quadruped_landing_b200 as ql
 p = ql.default_problem()
-nlp = ql.HybridNLP.from_problem(p)
 rng = np.random.default_rng(0)
 Z = ql.initial_guess(p)[None, :] + 1e-2 * rng.standard_normal((4096, p.n_nlp))
 Z[:, 19::20] = np.clip(Z[:, 19::20], 1e-3, 2e-2)
 res = {}
+CASES = [("block", ("f", "grad", "g", "jac"), "full"), ("block", ("g", "jac"), "g+J"), ("true", ("f", "grad", "g", "jac"), "TRUE"),
+         ("block", ("f", "grad", "g"), "f+grad+g"), ("block", ("g",), "g")]
+nlps = {pat: ql.HybridNLP.from_problem(p, pattern=pat) for pat in ("block", "true")}
 for Bt in (4096, 65536):
     Zt = torch.zeros((Bt, 1216), dtype=torch.float64, device="cuda")[:, :1215]     # padded rows: TMA load path
     Zt.copy_(torch.from_numpy(Z).cuda().repeat(Bt // 4096, 1))
-    out = nlp.eval_batch(Zt)
-    torch.cuda.synchronize()
-    for want in (("f", "grad", "g", "jac"), ("g", "jac")):
+    for pat, want, label in CASES:
+        nlp = nlps[pat]
+        out = nlp.eval_batch(Zt, want=want)
+        torch.cuda.synchronize()
         for _ in range(20):
             nlp.eval_batch(Zt, out=out, want=want)
         torch.cuda.synchronize()
@@ -41,7 +44,8 @@ for Bt in (4096, 65536):
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) / n)
-        res[f"{Bt}:{'+'.join(want)}"] = Bt / best * 1e3 / 1e6
+        res[f"{Bt // 1024}k:{label}"] = Bt / best * 1e3 / 1e6
+        del out
 print(json.dumps(res))
 ''' % ROOT
 
@@ -64,9 +68,9 @@ def main():
                 continue
             rows.append((name, json.loads(r.stdout.strip().splitlines()[-1])))
         keys = list(rows[0][1]) if rows else []
-        print(f"{'variant':28s}" + "".join(f"{k:>24s}" for k in keys) + "   (M evals/s)")
+        print(f"{'variant':16s}" + "".join(f"{k:>13s}" for k in keys) + "   (M evals/s)")
         for name, d in rows:
-            print(f"{name:28s}" + "".join(f"{d[k]:24.3f}" for k in keys))
+            print(f"{name:16s}" + "".join(f"{d[k]:13.2f}" for k in keys))
 
 
 if __name__ == "__main__":

@@ -11,8 +11,40 @@ __global__ void dfma_kernel(double* out, double a, double b, int iters)
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
+// dependent-chain latency of DADD / DMUL / DFMA: one warp per SM, 4096 dependent operations, clock64 around them
+template <int OP>
+__global__ void chain_kernel(double* out, long long* cyc, double a, double b)
+{
+    double x = threadIdx.x;
+    const long long t0 = clock64();
+#pragma unroll 64
+    for (int i = 0; i < 4096; ++i) {
+        if (OP == 0) x = __dadd_rn(x, a);
+        else if (OP == 1) x = __dmul_rn(x, a);
+        else x = __fma_rn(x, a, b);
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+template <int OP>
+static void chain(const char* name, double* d, int warps)
+{
+    long long* c; cudaMalloc(&c, 148 * sizeof(long long));
+    chain_kernel<OP><<<148, 32 * warps>>>(d, c, 1.0000001, 1e-9);
+    chain_kernel<OP><<<148, 32 * warps>>>(d, c, 1.0000001, 1e-9);
+    cudaDeviceSynchronize();
+    long long h[148]; cudaMemcpy(h, c, sizeof h, cudaMemcpyDeviceToHost);
+    printf("%s dependent chain, %2d warps/SM: %.2f cycles per operation\n", name, warps, h[0] / 4096.0);
+    cudaFree(c);
+}
 int main()
 {
+    {
+        double* d0; cudaMalloc(&d0, 148 * 1024 * sizeof(double));
+        for (int w : {1, 4, 8, 16}) { chain<0>("DADD", d0, w); chain<1>("DMUL", d0, w); chain<2>("DFMA", d0, w); }
+        cudaFree(d0);
+    }
     double* d; cudaMalloc(&d, 148 * 8 * 256 * sizeof(double));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int iters = 1 << 16;
