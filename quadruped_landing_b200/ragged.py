@@ -63,7 +63,6 @@ class RaggedEvaluator:
             idx = np.nonzero(class_of == c)[0]
             index.append(torch.from_numpy(idx).to(dev) if idx.size else None)
         # single launch: all problems, ordered by class, largest horizon first (the long evaluations start first)
-        order = np.argsort(-np.array([e.N for e in self.nlps])[class_of], kind="stable")
         by_class = sorted(range(len(self.nlps)), key=lambda c: -self.nlps[c].N)
         rank_of = np.empty(len(self.nlps), dtype=np.int64)
         rank_of[by_class] = np.arange(len(self.nlps))
@@ -79,8 +78,9 @@ class RaggedEvaluator:
         ``grad`` (Z layout), ``g``, ``jac`` and the offset tables; pass the returned dict back as ``out`` to reuse
         the output arrays.
 
-        Every class is one ``qlnlp_eval_ragged_device`` launch on its own stream: the kernel addresses each
-        problem's rows through the offset tables, so nothing is gathered or scattered."""
+        The whole mixed batch is ONE ``qlnlp_eval_ragged_classes`` launch (``single_launch=False``: one
+        ``qlnlp_eval_ragged_device`` launch per class on its own stream); the kernel addresses each problem's rows
+        through the offset tables, so nothing is gathered or scattered."""
         import torch
 
         dev = Z_flat.device

@@ -468,6 +468,34 @@ def test_handles_of_different_sizes_coexist():
     assert np.array_equal(a["jac"], b["jac"])
 
 
+def test_destroyed_handles_give_their_device_memory_back():
+    """Every path allocates lazily inside the handle (device scratch, pinned stages, worker pool, single-evaluation
+    cache, Hessian buffers): a create / use / destroy cycle must not leak device memory."""
+    import gc
+    p = ql.build_problem(N=21, k_trans=8)
+    Z = perturbed_batch(p, [ql.initial_guess(p)], 700, 1e-2, 3)
+
+    def cycle():
+        for pattern in ("block", "true"):
+            nlp = ql.HybridNLP.from_problem(p, pattern=pattern, hessian=True)
+            nlp.eval_batch_host(Z)                                   # host path: lanes, stages, pool, row plan
+            x = Z[0].copy()
+            nlp.eval_objective(x)                                    # single-evaluation cache
+            nlp.eval_hessian_lagrangian(np.empty(nlp.nnz_hess), x, 1.0, np.ones(nlp.m_nlp))
+            _dev_eval(nlp, Z[:8])
+            del nlp
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+    cycle()                                                          # module load, context growth, allocator pools
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(5):
+        cycle()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (8 << 20), f"{(free0 - free1) >> 20} MiB of device memory lost over 10 handles"
+
+
 def test_solver_loop_on_the_gpu_evaluator():
     """the solve() glue of moi.jl:46-103 driving the GPU evaluator through the four MOI callbacks
     with the SPARSE_TRUE structure (a few iterations; the callbacks must agree with the oracle at the iterate)."""
