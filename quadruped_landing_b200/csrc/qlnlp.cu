@@ -440,7 +440,18 @@ int set_carveout(const void* fn, int resident_blocks, size_t smem_per_block, siz
     std::lock_guard<std::mutex> lk(g_mu);
     size_t& need = g_need[fn];
     need = std::max(need, (size_t)resident_blocks * (smem_per_block + 1024));
-    const int pct = (int)std::min<size_t>(100, need * 100 / std::max<size_t>(1, smem_per_sm) + 2);
+    // The attribute is a percentage of the SM's UNIFIED L1 + shared memory (256 KB on sm_100; measured: 50 -> 132 KB,
+    // 58..65 -> 164 KB, 72 -> 196 KB, >= 79 -> 228 KB), rounded up to a carve-out the SM supports (0, 8, 16, 32, 64, 100,
+    // 132, 164, 196, 228 KB).  Ask for the smallest of those that holds `need`.  (Taking the percentage of the 228 KB
+    // shared-memory maximum instead left the kernel without a Jacobian on 228 KB of shared memory and 28 KB of L1:
+    // ncu launch__shared_mem_config_size; 46 % of its cost-table loads missed L1.  profiles/r02_kernel_ab.md)
+    static const size_t kCarveKB[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+    const size_t unified = (smem_per_sm + 65535) / 65536 * 65536;      // 228 KB -> 256 KB
+    size_t cfg = smem_per_sm;
+    for (size_t kb : kCarveKB)
+        if (kb * 1024 >= need) { cfg = std::min(cfg, kb * 1024); break; }
+    int pct = (int)std::min<size_t>(100, cfg * 100 / std::max<size_t>(1, unified));
+    pct = env_int("QLNLP_CARVEOUT_PCT", pct);          // tuning knob
     if (!std::getenv("QLNLP_MAX_CARVEOUT"))
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     return QLNLP_OK;
@@ -501,6 +512,9 @@ int ensure_device(qlnlp_handle h)
             int nb = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, h->smem[wj]));
             if (nb < 1) return fail(QLNLP_ECUDA, "kernel does not fit on an SM");
+            // never more resident warps than the kernel was compiled for (its __launch_bounds__)
+            if (wj == ql::JM_NONE) nb = std::min(nb, QL_NONE_WARPS);
+            else if (wj != ql::JM_BLOCK) nb = std::min(nb, QL_TRUE_WARPS);
             const char* env = std::getenv("QLNLP_BLOCKS_PER_SM");              // tuning knob: fewer resident warps per SM
             if (env) {
                 const int cap = std::atoi(env);
@@ -677,6 +691,8 @@ int ragged_table(const qlnlp_handle* hs, int ncls, const RagTable** out)
         int nb = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, t.smem[wj]));
         if (nb < 1) return fail(QLNLP_ECUDA, "kernel does not fit on an SM");
+        if (wj == ql::JM_NONE) nb = std::min(nb, QL_NONE_WARPS);
+        else if (wj != ql::JM_BLOCK) nb = std::min(nb, QL_TRUE_WARPS);
         const char* env = std::getenv("QLNLP_BLOCKS_PER_SM");
         if (env) {
             const int cap = std::atoi(env);

@@ -93,8 +93,23 @@ __device__ __forceinline__ void prefetch_l2(const void* gsrc, unsigned bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
-// g / grad rows are written once and never re-read by the kernel: streaming (evict-first) stores, +0.6 % in A/B runs
-#define QL_GST(ptr, v) __stcs((ptr), (v))
+// g / grad / f are written once and never re-read by the kernel.  SPARSE_BLOCK kernel: streaming stores (st.global.cs, +0.6 % over
+// plain stores).  The compact-output kernels re-read the cost table through L1 all the time (46 % of those loads miss it, ncu):
+// there the rows go out with L1::no_allocate (+1.2 % SPARSE_TRUE, +0.5 % f+grad+g, +1.5 % g only; -1 % on the SPARSE_BLOCK headline,
+// hence the split; profiles/r02_kernel_ab.md)
+template <bool NO_ALLOCATE>
+__device__ __forceinline__ void gst(double* p, double v)
+{
+    if (NO_ALLOCATE) asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+    else __stcs(p, v);
+}
+template <bool NO_ALLOCATE>
+__device__ __forceinline__ void gst(double2* p, double2 v)
+{
+    if (NO_ALLOCATE) asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    else __stcs(p, v);
+}
+#define QL_GST(ptr, v) gst<JM != JM_BLOCK>((ptr), (v))
 __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
 {
     asm volatile(
@@ -362,8 +377,8 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
             // boundary rows (constraints.jl:149-150) straight from the staged vector, one lane per row
             const double* x0 = P.x0 ? P.x0 + pi * QL_NX : x0_def;
             const double* xf = P.xf ? P.xf + pi * QL_NX : xf_def;
-            if (lane < QL_NX) grow[lane] = __dsub_rn(zbuf[lane], __ldg(x0 + lane));
-            if (lane < QL_NX - 1) grow[c.c_term + lane] = __dsub_rn(zbuf[(c.N - 1) * QL_NZK + lane], __ldg(xf + lane));
+            if (lane < QL_NX) QL_GST(grow + lane, __dsub_rn(zbuf[lane], __ldg(x0 + lane)));
+            if (lane < QL_NX - 1) QL_GST(grow + c.c_term + lane, __dsub_rn(zbuf[(c.N - 1) * QL_NZK + lane], __ldg(xf + lane)));
             __syncwarp();
         }
         for (int p = 0; p < c.npass; ++p) {
@@ -512,10 +527,10 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
                 // quirk Q4 (constraints.jl:269-273): branch on theta > 0
                 jtheta = (xk[2] > 0) ? __dmul_rn(-c.half_lb, co) : __dmul_rn(c.half_lb, co);
                 if (grow) {
-                    grow[c.c_cfirst + (k - 1)] = first_is_y1 ? xk[4] : xk[6];                                   // :58/:60
-                    if (k >= c.k_trans) grow[c.c_cother + (k - c.k_trans)] = first_is_y1 ? xk[6] : xk[4];      // :84/:86
-                    grow[c.c_body + (k - 1)] = __dsub_rn(xk[1], __dmul_rn(c.half_lb, fabs(s)));                 // :109
-                    if (k == c.N - 1) grow[c.c_fctrl] = __dadd_rn(__dadd_rn(uk[1], uk[3]), c.mbg);       // :154
+                    QL_GST(grow + c.c_cfirst + (k - 1), first_is_y1 ? xk[4] : xk[6]);                                   // :58/:60
+                    if (k >= c.k_trans) QL_GST(grow + c.c_cother + (k - c.k_trans), first_is_y1 ? xk[6] : xk[4]);      // :84/:86
+                    QL_GST(grow + c.c_body + (k - 1), __dsub_rn(xk[1], __dmul_rn(c.half_lb, fabs(s))));                 // :109
+                    if (k == c.N - 1) QL_GST(grow + c.c_fctrl, __dadd_rn(__dadd_rn(uk[1], uk[3]), c.mbg));       // :154
                 }
             }
 
@@ -649,7 +664,7 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
         // ---- 6. cost (accumulated in the reference's order above)
         if (P.f) {
             fsum = f_chain(fsum, fbuf);          // the last pass's terms
-            if (lane == 0) P.f[pi] = fsum;
+            if (lane == 0) QL_GST(P.f + pi, fsum);
         }
         b = nb;
     }

@@ -1,7 +1,7 @@
 """A/B timing of kernel variants on the GPU: each variant .so is timed in its own subprocess.
 
     python tools/ab_bench.py build   name=DEF1,DEF2 ...     (CPU box: compiles libqlnlp_<name>.so)
-    python tools/ab_bench.py run     name ...               (GPU box: times each, prints a table)
+    python tools/ab_bench.py run     name[@ENV=VALUE,...] ...   (GPU box: times each in its own process, prints a table)
 """
 import json
 import os
@@ -27,6 +27,9 @@ nlps = {pat: ql.HybridNLP.from_problem(p, pattern=pat) for pat in ("block", "tru
 for Bt in (4096, 65536):
     Zt = torch.zeros((Bt, 1216), dtype=torch.float64, device="cuda")[:, :1215]     # padded rows: TMA load path
     Zt.copy_(torch.from_numpy(Z).cuda().repeat(Bt // 4096, 1))
+    # like bench.py: the inputs of consecutive launches are distinct and together larger than L2 (4 x 40 MB at B = 4,096)
+    Zs = [Zt] if Bt > 4096 else [Zt] + [(Zt + 1e-6 * (j + 1)) for j in range(3)]
+    Zs = [z if z.stride(0) == 1216 else torch.zeros((Bt, 1216), dtype=torch.float64, device="cuda")[:, :1215].copy_(z) for z in Zs]
     for pat, want, label in CASES:
         nlp = nlps[pat]
         out = nlp.eval_batch(Zt, want=want)
@@ -39,8 +42,8 @@ for Bt in (4096, 65536):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             n = 50 if Bt == 4096 else 8
             e0.record()
-            for _ in range(n):
-                nlp.eval_batch(Zt, out=out, want=want)
+            for i in range(n):
+                nlp.eval_batch(Zs[i %% len(Zs)], out=out, want=want)
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) / n)
@@ -59,18 +62,20 @@ def main():
             print(build.build_variant(name, [d for d in defs.split(",") if d]))
     else:
         rows = []
-        for name in args:
-            lib = os.path.join(ROOT, "quadruped_landing_b200", f"libqlnlp_{name}.so" if name != "default" else "libqlnlp.so")
+        for name in args:                  # name[@ENV=VALUE,...]: the variant's library, with extra environment
+            var, _, envs = name.partition("@")
+            lib = os.path.join(ROOT, "quadruped_landing_b200", f"libqlnlp_{var}.so" if var != "default" else "libqlnlp.so")
             env = dict(os.environ, QLNLP_LIB=lib)
+            env.update(kv.split("=", 1) for kv in envs.split(",") if kv)
             r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
             if r.returncode != 0:
                 print(name, "FAILED", r.stderr[-500:])
                 continue
             rows.append((name, json.loads(r.stdout.strip().splitlines()[-1])))
         keys = list(rows[0][1]) if rows else []
-        print(f"{'variant':16s}" + "".join(f"{k:>13s}" for k in keys) + "   (M evals/s)")
+        print(f"{'variant':32s}" + "".join(f"{k:>13s}" for k in keys) + "   (M evals/s)")
         for name, d in rows:
-            print(f"{name:16s}" + "".join(f"{d[k]:13.2f}" for k in keys))
+            print(f"{name:32s}" + "".join(f"{d[k]:13.2f}" for k in keys))
 
 
 if __name__ == "__main__":
