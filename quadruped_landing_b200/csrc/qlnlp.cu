@@ -817,6 +817,7 @@ int launch_hessian(qlnlp_handle h, int64_t B, const double* Z, int64_t ldz, cons
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, QL_LANES, smem));
         if (nb < 1) return fail(QLNLP_ECUDA, "Hessian kernel does not fit on an SM");
         h->hess_blocks_per_sm = nb;
+        if (int rc = set_carveout(fn, nb, smem, h->smem_per_sm)) return rc;      // the rest of the SM's memory is L1 (cost table)
     }
     ql::HessLaunch P;
     P.c = c;

@@ -248,6 +248,7 @@ __device__ __forceinline__ void stage_z(const double* __restrict__ Zrow, unsigne
 // fsum + t[0] + t[1] + ... + t[31], strictly left to right (costs.jl:9-15); lanes without a knot have stored -0.0
 __device__ __forceinline__ double f_chain(double fsum, const double* fbuf)
 {
+    // (forcing all 16 loads ahead of the adds with volatile asm changes nothing measurable: profiles/r02_kernel_ab.md)
     const double2* f2 = reinterpret_cast<const double2*>(fbuf);
 #pragma unroll
     for (int s = 0; s < QL_LANES / 2; ++s) {
