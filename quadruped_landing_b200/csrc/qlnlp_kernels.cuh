@@ -334,9 +334,9 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
         else cp_async_wait_all();
         __syncwarp();
         double fsum = 0.0;
-        // the kernels without the SPARSE_BLOCK stream are latency-bound: take the next ticket now, so that the atomic's
-        // round trip is hidden behind this evaluation (the SPARSE_BLOCK kernel has no register to spare for it)
-        // With a cost / gradient part the ticket is only drawn here and read after the first pass's cost section, when
+        // The kernels without the SPARSE_BLOCK stream are latency-bound: they draw the next ticket now, so that the
+        // atomic's round trip is hidden behind this evaluation (the SPARSE_BLOCK kernel has no register to spare for it).
+        // With a cost / gradient part the ticket is only DRAWN here and read after the first pass's cost section, when
         // the atomic has returned.  The short g-only evaluation reads it at once: reading it late made that launch
         // bimodal (265 or 349 M evals/s from one process to the next, profiles/r02_kernel_ab.md), at once it is steady.
         const bool late_ticket = JM != JM_BLOCK && (P.f || P.grad);
