@@ -433,6 +433,16 @@ int ensure_pool(qlnlp_handle h)
     return QLNLP_OK;
 }
 
+// Dynamic shared memory to ask for so that `per_sm` CTAs fit on an SM but `per_sm + 1` never do, whatever carve-out the
+// kernel runs on (see launch(): programmatic dependent launch and spare CTA slots).
+size_t padded_smem(size_t smem_per_sm, size_t smem_optin, int per_sm, size_t smem)
+{
+    if (!env_flag("QLNLP_PAD_SMEM", true)) return smem;
+    const size_t pad = (smem_per_sm / (size_t)(per_sm + 1) - 1024 + 128) & ~(size_t)127;
+    if (pad > smem && (size_t)per_sm * (pad + 1024) <= smem_per_sm && pad <= smem_optin) return pad;
+    return smem;
+}
+
 int set_carveout(const void* fn, int resident_blocks, size_t smem_per_block, size_t smem_per_sm)
 {
     static std::map<const void*, size_t> g_need;
@@ -524,7 +534,11 @@ int ensure_device(qlnlp_handle h)
             // Shared memory the resident warps really need: whatever the SM has beyond that serves as L1 (the cost
             // table and the boundary states are re-read by every warp).  The attribute belongs to the FUNCTION, so it
             // only ever grows (handles of other horizons share it).
-            if (int rc = set_carveout(fn, (wj == ql::JM_BLOCK && !env) ? std::min(nb, 6) : nb, h->smem[wj], h->smem_per_sm)) return rc;
+            {
+                const int res = (wj == ql::JM_BLOCK && !env) ? std::min(nb, 6) : nb;
+                const size_t per_block = (wj == ql::JM_BLOCK) ? padded_smem(h->smem_per_sm, (size_t)prop.sharedMemPerBlockOptin, res, h->smem[wj]) : h->smem[wj];
+                if (int rc = set_carveout(fn, res, per_block, h->smem_per_sm)) return rc;
+            }
         }
     }
     for (auto& ln : h->lanes) {
@@ -636,11 +650,31 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
         it = h->tickets.emplace(stream, d).first;
     }
     P.ticket = it->second;
+    // With programmatic dependent launch the next grid's CTAs are placed as soon as an SM has room for one.  The
+    // SPARSE_BLOCK kernel runs on fewer CTAs per SM than would fit (5 or 6 of up to 7 by shared memory): a spare slot
+    // would take a CTA of the next grid while this grid is still running at full strength, and the next grid would
+    // start out unevenly spread over the SMs (measured: -5 % on the headline once another handle had raised the
+    // kernel's carve-out to 228 KB).  Ask for enough shared memory per CTA that per_sm + 1 of them never fit.
+    // (Only that kernel: the others are capped by their registers, and padding them would cost L1.)
+    const size_t smem_launch = (wj == ql::JM_BLOCK) ? padded_smem(h->smem_per_sm, h->smem_optin, per_sm, smem) : smem;
     void* args[] = {&P};
-    CUDA_TRY(cudaLaunchKernel(kernel_fn(wj, fast, rg != nullptr), dim3(grid), dim3(QL_LANES), args, smem, stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(QL_LANES);
+    cfg.dynamicSmemBytes = smem_launch;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    // programmatic dependent launch: back-to-back evaluations on a stream overlap the next grid's start-up with this
+    // grid's drain (B = 4,096: +1 % full evaluation, +4..6 % for the compact-output kernels; the kernel waits for its
+    // predecessors before it touches any data, see griddepcontrol.wait in eval_kernel).  QLNLP_PDL=0 turns it off.
+    cfg.numAttrs = env_flag("QLNLP_PDL", true) ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelExC(&cfg, kernel_fn(wj, fast, rg != nullptr), args));
     h->last_launch[0] = grid;
     h->last_launch[1] = QL_LANES;
-    h->last_launch[2] = (int64_t)smem;
+    h->last_launch[2] = (int64_t)smem_launch;
     h->last_launch[3] = per_sm;
     h->last_launch[4] = h->sm_count;
     return QLNLP_OK;
@@ -699,7 +733,11 @@ int ragged_table(const qlnlp_handle* hs, int ncls, const RagTable** out)
             if (cap >= 1 && cap < nb) nb = cap;
         }
         t.blocks_per_sm[wj] = nb;
-        if (int rc = set_carveout(fn, (wj == ql::JM_BLOCK && !env) ? std::min(nb, 6) : nb, t.smem[wj], lead->smem_per_sm)) return rc;
+        {
+            const int res = (wj == ql::JM_BLOCK && !env) ? std::min(nb, 6) : nb;
+            const size_t per_block = (wj == ql::JM_BLOCK) ? padded_smem(lead->smem_per_sm, lead->smem_optin, res, t.smem[wj]) : t.smem[wj];
+            if (int rc = set_carveout(fn, res, per_block, lead->smem_per_sm)) return rc;
+        }
     }
     *out = &lead->rag_tables.emplace(key, t).first->second;
     return QLNLP_OK;

@@ -319,15 +319,21 @@ __global__ void __launch_bounds__(QL_LANES, JM == JM_NONE ? QL_NONE_WARPS : (JM 
     };
     auto take_get = [&](unsigned t) -> long long { return (long long)__shfl_sync(0xffffffffu, t, 0); };
     auto take = [&]() -> long long { return take_get(take_issue()); };
-    long long b = take();
-    long long nb = P.B;
-    if (b < P.B) stage_z(zrow_of(b), zaddr, mbar, n_of(b), lane, zbulk);
+    // Programmatic dependent launch (the launcher sets the attribute on request): the next grid on the stream may be
+    // scheduled into the SM slots this grid's warps give up while they drain; everything of it that touches data a
+    // predecessor may have written - the work counter first of all - comes after griddepcontrol.wait, which returns
+    // when every prerequisite grid has completed and flushed.  Without the attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (JM == JM_BLOCK && !RAGGED) {
-        // the segment plan lives in shared memory: one 16-byte record per segment
+        // the segment plan lives in shared memory: one 16-byte record per segment (a table of the handle, written once)
         const int4* src = reinterpret_cast<const int4*>(P.segs);
         int4* dst = reinterpret_cast<int4*>(plan);
         for (int i = lane; i < P.nseg; i += QL_LANES) dst[i] = __ldg(src + i);
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    long long b = take();
+    long long nb = P.B;
+    if (b < P.B) stage_z(zrow_of(b), zaddr, mbar, n_of(b), lane, zbulk);
 
     while (b < P.B) {
         if (zbulk) { mbar_wait(mbar, zphase); zphase ^= 1u; }
