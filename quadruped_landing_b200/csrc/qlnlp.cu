@@ -972,6 +972,7 @@ int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
 
+    const bool vals_first = env_flag("QLNLP_HOST_VALS_FIRST", true);
     auto enqueue = [&](int64_t i) -> int {
         const double t0 = now();
         HostLane& ln = h->lanes[i % nlanes];
@@ -990,13 +991,19 @@ int eval_host_impl(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io)
         d.g = io->g ? ln.g : nullptr; d.ldg = ldg_d;
         d.jac = io->jac ? ln.jac : nullptr; d.ldjac = compact ? h->ldv_e : ldjac_d;
         if (int rc = h->kin ? launch_kin(h, nb, &d, s) : launch(h, nb, &d, s, compact ? ql::JM_VALS : -1)) return rc;
+        // the staged values go first: the row builder only waits for them, f / grad / g land in the caller's arrays
+        // by DMA while it works (the lanes are synchronised before the call returns)
+        if (compact && vals_first) {
+            CUDA_TRY(cudaMemcpyAsync(ln.stage, ln.jac, sizeof(double) * nb * h->ldv_e, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaEventRecord(ln.done, s));
+        }
         if (io->f) CUDA_TRY(cudaMemcpyAsync(io->f + b0, ln.f, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
         if (io->grad) CUDA_TRY(copy_rows(io->grad + b0 * io->ldgrad, io->ldgrad, ln.grad, ldgrad_d, c.n_nlp, nb, cudaMemcpyDeviceToHost, s));
         if (io->g) CUDA_TRY(copy_rows(io->g + b0 * io->ldg, io->ldg, ln.g, ldg_d, m_out, nb, cudaMemcpyDeviceToHost, s));
-        if (compact) {
+        if (compact && !vals_first) {
             CUDA_TRY(cudaMemcpyAsync(ln.stage, ln.jac, sizeof(double) * nb * h->ldv_e, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaEventRecord(ln.done, s));
-        } else if (io->jac) {
+        } else if (!compact && io->jac) {
             CUDA_TRY(copy_rows(io->jac + b0 * io->ldjac, io->ldjac, ln.jac, ldjac_d, nnz_b, nb, cudaMemcpyDeviceToHost, s));
         }
         h->stat_t_enqueue += now() - t0;
