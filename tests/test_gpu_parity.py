@@ -566,6 +566,49 @@ def test_launches_can_be_captured_in_a_cuda_graph(dflt, golden):
         assert torch.equal(out[k], eager[k]), k
 
 
+def test_back_to_back_launches_respect_stream_order(dflt, golden):
+    """Evaluations are launched with programmatic dependent launch: the next grid may be scheduled while the previous
+    one drains, so the kernel itself has to wait for its predecessors before it touches data.  Queue, without any
+    host synchronisation, (a) two evaluations of different inputs into the same outputs, (b) a torch kernel that
+    reads the outputs between two evaluations, (c) a torch kernel that rewrites the inputs between two evaluations,
+    many times over, and compare every snapshot with evaluations done one at a time."""
+    p, nlp, o = dflt
+    B = 1500                                          # a short grid: the hand-over between two grids is most of the run
+    Za = perturbed_batch(p, _bases(p, golden), B, 1e-2, 5)
+    Zb = perturbed_batch(p, _bases(p, golden), B, 2e-2, 6)
+    pad = lambda Z: torch.zeros((B, 1216), dtype=torch.float64, device="cuda")[:, :1215].copy_(torch.from_numpy(Z))
+    A, Bm = pad(Za), pad(Zb)
+    ra = {k: v.clone() for k, v in nlp.eval_batch(A).items()}
+    torch.cuda.synchronize()
+    rb = {k: v.clone() for k, v in nlp.eval_batch(Bm).items()}
+    torch.cuda.synchronize()
+    delta = 1e-3 * torch.randn((B, 1215), dtype=torch.float64, device="cuda")
+    W = A.clone()                                     # rewritten in place below
+    Wp = pad(Za)
+    Wp += delta
+    rw = {k: v.clone() for k, v in nlp.eval_batch(Wp).items()}
+    torch.cuda.synchronize()
+    out = {k: torch.zeros_like(v) for k, v in ra.items()}
+    snaps = []
+    for _ in range(6):
+        nlp.eval_batch(A, out=out)                    # (a)
+        nlp.eval_batch(Bm, out=out)
+        snaps.append(("b", {k: v.clone() for k, v in out.items()}))       # (b) torch reads what the 2nd launch wrote ...
+        nlp.eval_batch(A, out=out)                    # ... and the 3rd overwrites it
+        snaps.append(("a", {k: v.clone() for k, v in out.items()}))
+        W.copy_(A)                                    # (c) torch rewrites the input of the next launch
+        W += delta
+        Wv = torch.zeros((B, 1216), dtype=torch.float64, device="cuda")[:, :1215]
+        Wv.copy_(W)
+        nlp.eval_batch(Wv, out=out)
+        snaps.append(("w", {k: v.clone() for k, v in out.items()}))
+    torch.cuda.synchronize()
+    ref = {"a": ra, "b": rb, "w": rw}
+    for tag, snap in snaps:
+        for k in snap:
+            assert torch.equal(snap[k], ref[tag][k]), (tag, k)
+
+
 def test_eval_all_and_the_x_cache(dflt, golden):
     """qlnlp_eval_all = the four callbacks with one launch; the callbacks themselves are served from the last
     evaluation when x is unchanged (moi.jl:1-24 calls them one by one) -- and must notice an x changed IN PLACE."""
