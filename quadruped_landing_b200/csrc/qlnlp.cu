@@ -561,6 +561,34 @@ int ensure_device(qlnlp_handle h)
     return QLNLP_OK;
 }
 
+// Work counter of a stream (launches on one stream are ordered, so they can share it; the kernel's last CTA re-arms
+// it).  Concurrent launches of the handle on different streams get different counters.
+int stream_ticket(qlnlp_handle h, cudaStream_t stream, unsigned** out)
+{
+    auto it = h->tickets.find(stream);
+    if (it == h->tickets.end()) {
+        if (h->ticket_pool_used >= TICKET_POOL) {
+            // Every counter of the pre-zeroed pool belongs to a stream.  Streams come and go (torch pools), so wait
+            // for the handle's outstanding launches and start the pool over rather than allocating (an allocation
+            // here would make the launch illegal inside a CUDA-graph capture, and a faulted kernel could leave a
+            // counter un-re-armed: the reset also heals that).
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(stream, &cap);
+            if (cap != cudaStreamCaptureStatusNone)
+                return fail(QLNLP_EINVAL, "more than %d streams used with this handle: cannot recycle work counters during a graph capture", TICKET_POOL);
+            CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemset(h->ticket_pool, 0, 128 * TICKET_POOL));
+            CUDA_TRY(cudaDeviceSynchronize());
+            h->tickets.clear();
+            h->ticket_pool_used = 0;
+        }
+        unsigned* d = h->ticket_pool + 32 * h->ticket_pool_used++;      // zeroed (and synchronised) at set-up
+        it = h->tickets.emplace(stream, d).first;
+    }
+    *out = it->second;
+    return QLNLP_OK;
+}
+
 int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t stream, int jm_force = -1,
            const qlnlp_ragged_io* rg = nullptr, const RagTable* table = nullptr, const int32_t* class_of = nullptr)
 {
@@ -627,29 +655,7 @@ int launch(qlnlp_handle h, int64_t B, const qlnlp_batch_io* io, cudaStream_t str
         const int gsz = std::atoi(e);
         if (gsz >= 1 && gsz <= resident) grid = (int)std::min<int64_t>(B, gsz);
     }
-    // work counter of this stream (launches on one stream are ordered, so they can share it; the kernel's last CTA
-    // re-arms it).  Concurrent launches of the handle on different streams get different counters.
-    auto it = h->tickets.find(stream);
-    if (it == h->tickets.end()) {
-        if (h->ticket_pool_used >= TICKET_POOL) {
-            // Every counter of the pre-zeroed pool belongs to a stream.  Streams come and go (torch pools), so wait
-            // for the handle's outstanding launches and start the pool over rather than allocating (an allocation
-            // here would make the launch illegal inside a CUDA-graph capture, and a faulted kernel could leave a
-            // counter un-re-armed: the reset also heals that).
-            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-            cudaStreamIsCapturing(stream, &cap);
-            if (cap != cudaStreamCaptureStatusNone)
-                return fail(QLNLP_EINVAL, "more than %d streams used with this handle: cannot recycle work counters during a graph capture", TICKET_POOL);
-            CUDA_TRY(cudaDeviceSynchronize());
-            CUDA_TRY(cudaMemset(h->ticket_pool, 0, 128 * TICKET_POOL));
-            CUDA_TRY(cudaDeviceSynchronize());
-            h->tickets.clear();
-            h->ticket_pool_used = 0;
-        }
-        unsigned* d = h->ticket_pool + 32 * h->ticket_pool_used++;      // zeroed (and synchronised) at set-up
-        it = h->tickets.emplace(stream, d).first;
-    }
-    P.ticket = it->second;
+    if (int rc = stream_ticket(h, stream, &P.ticket)) return rc;
     // With programmatic dependent launch the next grid's CTAs are placed as soon as an SM has room for one.  The
     // SPARSE_BLOCK kernel runs on fewer CTAs per SM than would fit (5 or 6 of up to 7 by shared memory): a spare slot
     // would take a CTA of the next grid while this grid is still running at full strength, and the next grid would
@@ -868,6 +874,7 @@ int launch_hessian(qlnlp_handle h, int64_t B, const double* Z, int64_t ldz, cons
     P.B = B;
     P.bulk = ((reinterpret_cast<uintptr_t>(H) & 15) == 0 && (ldh & 1) == 0) ? 1 : 0;
     P.zbulk = ((reinterpret_cast<uintptr_t>(Z) & 15) == 0 && (ldz & 1) == 0) ? 1 : 0;
+    if (int rc = stream_ticket(h, stream, &P.ticket)) return rc;
     const int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count * h->hess_blocks_per_sm);
     void* args[] = {&P};
     CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(QL_LANES), args, smem, stream));
