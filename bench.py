@@ -521,10 +521,11 @@ def run_gpu(args):
 
     # ---- extras first: they also bring the GPU to its working clocks before the headline starts
     if not args.no_extras:
-        guarded("variants", lambda: section_variants(cx, prob, host_sets))
-        guarded("c3", lambda: section_c3(cx, prob))
-        guarded("c4", lambda: section_c4(cx))
-        guarded("c5", lambda: section_c5(cx, prob))
+        skip = set(os.environ.get("QL_BENCH_SKIP", "").split(","))      # diagnosis only: leave sections out
+        for name, fn in (("variants", lambda: section_variants(cx, prob, host_sets)), ("c3", lambda: section_c3(cx, prob)),
+                         ("c4", lambda: section_c4(cx)), ("c5", lambda: section_c5(cx, prob))):
+            if name not in skip:
+                guarded(name, fn)
 
     # ---- headline: device-resident throughput of C2 ---------------------------------------------------------
     Zs = [padded(torch, z, dev) for z in host_sets]
