@@ -16,11 +16,12 @@ for line in sass.splitlines():
     if m and cur:
         funcs[cur].append((m.group(1), m.group(2).strip()))
 demangle = lambda n: subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip().replace("void ", "").replace("(ql::Launch)", "").replace("(ql::HessLaunch)", "").replace("(int)", "").replace("(bool)", "")
-OPS = ["UBLKCP", "SYNCS", "UBLKPF", "DADD", "DMUL", "DFMA", "STS", "LDS", "STG", "LDG"]
+OPS = ["UBLKCP", "SYNCS", "UBLKPF", "PREEXIT", "ACQBULK", "DADD", "DMUL", "DFMA", "STS", "LDS", "STG", "LDG"]
 print("# SASS evidence (round 2, final build) -- `cuobjdump -sass quadruped_landing_b200/libqlnlp.so`, sm_100a cubin only\n")
 print("Regenerate with `python tools/sass_excerpt.py`.  Demangled: `ql::eval_kernel<JM, FASTDIV, RAGGED>`; JM 0 = no Jacobian, 1 = SPARSE_BLOCK,")
 print("2 = SPARSE_TRUE, 3 = VALS (host path); `ql::hess_kernel<FASTDIV>` = Lagrangian Hessian.  `UBLKCP` = TMA bulk copy (`cp.async.bulk`),")
-print("`SYNCS` = mbarrier operations, `UBLKPF` = bulk L2 prefetch; the RK4 / dual arithmetic is DADD / DMUL (un-fused by construction), DFMA")
+print("`SYNCS` = mbarrier operations, `UBLKPF` = bulk L2 prefetch, `PREEXIT` / `ACQBULK` = `griddepcontrol.launch_dependents` / `.wait`")
+print("(programmatic dependent launch); the RK4 / dual arithmetic is DADD / DMUL (un-fused by construction), DFMA")
 print("appears only inside the exact reciprocal division and sincos.\n")
 print("| kernel | instructions | KB | " + " | ".join(OPS) + " | registers |")
 print("|---|---|---|" + "---|" * (len(OPS) + 1))
