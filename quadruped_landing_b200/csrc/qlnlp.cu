@@ -443,6 +443,17 @@ size_t padded_smem(size_t smem_per_sm, size_t smem_optin, int per_sm, size_t sme
     return smem;
 }
 
+// cudaFuncAttributePreferredSharedMemoryCarveout value for `need` bytes of shared memory per SM (see set_carveout)
+int carveout_pct(size_t need, size_t smem_per_sm)
+{
+    static const size_t kCarveKB[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+    const size_t unified = (smem_per_sm + 65535) / 65536 * 65536;      // 228 KB -> 256 KB
+    size_t cfg = smem_per_sm;
+    for (size_t kb : kCarveKB)
+        if (kb * 1024 >= need) { cfg = std::min(cfg, kb * 1024); break; }
+    return (int)std::min<size_t>(100, cfg * 100 / std::max<size_t>(1, unified));
+}
+
 int set_carveout(const void* fn, int resident_blocks, size_t smem_per_block, size_t smem_per_sm)
 {
     static std::map<const void*, size_t> g_need;
@@ -455,12 +466,7 @@ int set_carveout(const void* fn, int resident_blocks, size_t smem_per_block, siz
     // 132, 164, 196, 228 KB).  Ask for the smallest of those that holds `need`.  (Taking the percentage of the 228 KB
     // shared-memory maximum instead left the kernel without a Jacobian on 228 KB of shared memory and 28 KB of L1:
     // ncu launch__shared_mem_config_size; 46 % of its cost-table loads missed L1.  profiles/r02_kernel_ab.md)
-    static const size_t kCarveKB[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
-    const size_t unified = (smem_per_sm + 65535) / 65536 * 65536;      // 228 KB -> 256 KB
-    size_t cfg = smem_per_sm;
-    for (size_t kb : kCarveKB)
-        if (kb * 1024 >= need) { cfg = std::min(cfg, kb * 1024); break; }
-    int pct = (int)std::min<size_t>(100, cfg * 100 / std::max<size_t>(1, unified));
+    int pct = carveout_pct(need, smem_per_sm);
     pct = env_int("QLNLP_CARVEOUT_PCT", pct);          // tuning knob
     if (!std::getenv("QLNLP_MAX_CARVEOUT"))
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -1836,6 +1842,18 @@ int qlnlp_debug_host_times(qlnlp_handle h, double out[4])
     if (int rc = check_handle(h)) return rc;
     qlnlp_handle s = first(h);
     out[0] = s->stat_t_total; out[1] = s->stat_t_enqueue; out[2] = s->stat_t_wait; out[3] = s->stat_t_build;
+    return QLNLP_OK;
+}
+
+/* Launch geometry arithmetic, checkable without a device: out[0] = dynamic shared memory a SPARSE_BLOCK launch asks for
+ * so that per_sm CTAs fit on an SM but per_sm + 1 never do, out[1] = the carve-out percentage requested for per_sm such
+ * CTAs (not part of the public header: tests/test_cabi_cpu.py) */
+int qlnlp_debug_launch_geometry(int64_t smem_per_sm, int64_t smem_optin, int per_sm, int64_t smem, int64_t out[2])
+{
+    if (!out || smem_per_sm <= 0 || per_sm < 1 || smem < 0) return fail(QLNLP_EINVAL, "bad arguments");
+    const size_t padded = padded_smem((size_t)smem_per_sm, (size_t)smem_optin, per_sm, (size_t)smem);
+    out[0] = (int64_t)padded;
+    out[1] = carveout_pct((size_t)per_sm * (padded + 1024), (size_t)smem_per_sm);
     return QLNLP_OK;
 }
 

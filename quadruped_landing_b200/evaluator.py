@@ -40,7 +40,8 @@ EXPORTED_SYMBOLS = (
     "qlnlp_hessian_nnz", "qlnlp_hessian_structure", "qlnlp_eval_hessian_lagrangian", "qlnlp_eval_hessian_batch_device",
     "qlnlp_initial_guess_batch_device",
 )
-_DEBUG_SYMBOLS = ("qlnlp_debug_segments", "qlnlp_debug_vals_map", "qlnlp_debug_build_rows", "qlnlp_debug_host_times")
+_DEBUG_SYMBOLS = ("qlnlp_debug_segments", "qlnlp_debug_vals_map", "qlnlp_debug_build_rows", "qlnlp_debug_host_times",
+                  "qlnlp_debug_launch_geometry")
 
 
 class QlnlpError(RuntimeError):
@@ -111,6 +112,7 @@ def load_library(rebuild_if_stale: bool = True):
     L.qlnlp_debug_vals_map.argtypes = [vp, vp, C.c_int64, i64p]
     L.qlnlp_debug_build_rows.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int, C.c_int]
     L.qlnlp_debug_host_times.argtypes = [vp, C.POINTER(C.c_double)]
+    L.qlnlp_debug_launch_geometry.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int64, C.POINTER(C.c_int64)]
     L.qlnlp_create_multi.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]
     L.qlnlp_devices.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
     L.qlnlp_shard_bounds.argtypes = [C.c_int64, C.c_int, C.c_int, i64p, i64p]

@@ -46,6 +46,31 @@ def test_host_queries_work_without_a_device():
     assert nlp.xinds[1][0] == 21 and nlp.uinds[0][0] == 16 and nlp.modes[19] == 1 and nlp.modes[20] == 3
 
 
+def test_launch_geometry_arithmetic_for_the_b200():
+    """Two integer rules of the launcher that went wrong silently once (profiles/r02_kernel_ab.md): the shared-memory
+    carve-out is a percentage of the UNIFIED 256 KB (72..76 % selects the 196 KB configuration, 79 % and more 228 KB),
+    and a SPARSE_BLOCK launch asks for so much shared memory that per_sm CTAs fit on an SM but per_sm + 1 never do."""
+    import ctypes as C
+    from quadruped_landing_b200.evaluator import load_library
+    lib = load_library()
+    per_sm_bytes, optin = 233472, 232448                      # sm_100: 228 KB per SM, 227 KB per block
+    out = (C.c_int64 * 2)()
+    for per_sm, smem in ((6, 27776), (5, 27776), (8, 27776), (4, 40000)):
+        assert lib.qlnlp_debug_launch_geometry(per_sm_bytes, optin, per_sm, smem, out) == 0
+        padded, pct = out[0], out[1]
+        assert padded >= smem and padded % 128 == 0 and padded <= optin
+        assert per_sm * (padded + 1024) <= per_sm_bytes                     # per_sm CTAs fit ...
+        if padded > smem:
+            assert (per_sm + 1) * (padded + 1024) > per_sm_bytes            # ... and one more never does
+        need_kb = per_sm * (padded + 1024) / 1024
+        cfg_kb = min(k for k in (0, 8, 16, 32, 64, 100, 132, 164, 196, 228) if k >= need_kb)
+        # what the driver does with the percentage (measured on a B200): bytes = pct % of 256 KB, rounded UP to a configuration
+        chosen = min(k for k in (0, 8, 16, 32, 64, 100, 132, 164, 196, 228) if k * 1024 >= pct * 262144 // 100)
+        assert chosen == cfg_kb, (per_sm, smem, padded, pct, chosen, cfg_kb)
+    assert lib.qlnlp_debug_launch_geometry(per_sm_bytes, optin, 6, 27776, out) == 0
+    assert (out[0], out[1]) == (32384, 76)                                   # the default instance's headline launch
+
+
 def test_reference_constructor_signature():
     p = ql.default_problem()
     xi, xt = ql.default_states()
